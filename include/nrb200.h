@@ -1,0 +1,133 @@
+/*
+ * nrb200.h -- C-ABI of libnrb200.so, the B200 (sm_100a) candidate-retrieval library.
+ *
+ * This is the drop-in boundary below the Python `faiss`-compatible surface
+ * (newsrecommend_b200/faiss.py). The reference has no FFI of its own: its hot path
+ * (/root/reference/Retrieval.py) reaches native code only through the SWIG-wrapped `faiss`
+ * module, so each entry point below cites the reference call site (Retrieval.py:LINE) and the
+ * faiss routine it stands in for. All pointers are plain DEVICE pointers unless the name ends in
+ * `_host`; sizes are element counts; `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream). Every function returns 0 on success and a negative code on failure, never throws,
+ * and leaves a message retrievable with nrb_last_error(). There is no CPU fallback: on a
+ * machine without an sm_100 GPU the compute entry points return NRB_ERR_NO_DEVICE.
+ */
+#ifndef NRB200_H
+#define NRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRB_OK 0
+#define NRB_ERR_INVALID -1   /* bad argument */
+#define NRB_ERR_CUDA -2      /* CUDA runtime / driver error */
+#define NRB_ERR_NO_DEVICE -3 /* no sm_100 device */
+#define NRB_ERR_WORKSPACE -4 /* workspace too small */
+
+#define NRB_METRIC_INNER_PRODUCT 0 /* faiss.METRIC_INNER_PRODUCT */
+#define NRB_METRIC_L2 1            /* faiss.METRIC_L2 (squared L2, as Retrieval.py:16,25) */
+
+#define NRB_PATH_AUTO 0
+#define NRB_PATH_SIMT 1 /* fp32 CUDA-core kernels */
+#define NRB_PATH_TC 2   /* tcgen05 3xTF32 kernels */
+
+#define NRB_MAX_K 128 /* largest k / nprobe supported by the selection stage */
+
+/* A row-major matrix in its device ("packed") form, produced by nrb_pack_rows():
+ *   raw  [n, kp]  fp32 rows zero-padded from d to kp columns (kp % 32 == 0)
+ *   hi   [n, kp]  tf32(raw)            (cvt.rna, low 13 mantissa bits zero)
+ *   lo   [n, kp]  tf32(raw - hi)
+ *   norms[n]      squared L2 norms (fp32)
+ * raw feeds the SIMT kernels, hi/lo feed the 3xTF32 tcgen05 kernels via TMA. */
+typedef struct nrb_matrix {
+    const float* raw;
+    const float* hi;
+    const float* lo;
+    const float* norms;
+    int64_t n;
+    int32_t d;
+    int32_t kp;
+} nrb_matrix;
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+int nrb_version(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf. */
+int nrb_last_error(char* buf, int buflen);
+/* sm count and compute capability of the current device. */
+int nrb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t nrb_launch_count(void);
+
+/* ---- K0: pack ---------------------------------------------------------------------------- */
+/* Replaces the numpy cast + contiguity at Retrieval.py:8,17,31 (and IndexFlatCodes::add's
+ * memcpy, Retrieval.py:26): x is fp32 [n, d] with row stride ldx elements. Any of raw/hi/lo/
+ * norms may be NULL. */
+int nrb_pack_rows(const float* x, int64_t n, int32_t d, int64_t ldx, int32_t kp, float* raw,
+                  float* hi, float* lo, float* norms, void* stream);
+/* dst[i, :] = src[idx[i], :] for rows of `width` floats (width % 4 == 0). Builds the
+ * list-contiguous IVF planes (ArrayInvertedLists, Retrieval.py:23) and query groups. */
+int nrb_gather_rows(const float* src, int32_t width, const int32_t* idx, int64_t n, float* dst,
+                    void* stream);
+/* dst[i] = src[idx[i]] for 64-bit ids (external ids in list order). */
+int nrb_gather_i64(const int64_t* src, const int32_t* idx, int64_t n, int64_t* dst, void* stream);
+/* faiss.normalize_L2 (fvec_renorm_L2): in place, zero rows untouched. */
+int nrb_normalize_l2(float* x, int64_t n, int32_t d, int64_t ldx, void* stream);
+
+/* ---- K2: exact top-k (IndexFlat::search -> knn_inner_product / knn_L2sqr) ------------------ */
+/* Replaces IndexFlatL2/IndexFlatIP.search at Retrieval.py:21,32 and the k-means assignment
+ * search inside Clustering::train (Retrieval.py:18). D f32[nq,k] best-first (IP descending,
+ * L2 ascending squared distance clamped at 0), I i64[nq,k] = row index + id_base; missing
+ * results are I = -1, D = -FLT_MAX (IP) / +FLT_MAX (L2). 1 <= k <= NRB_MAX_K. */
+size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp);
+int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
+                    int64_t id_base, float* D, int64_t* I, void* workspace,
+                    size_t workspace_bytes, int32_t path, void* stream);
+
+/* ---- K1b: k-means centroid update (Clustering.cpp compute_centroids) ---------------------- */
+/* Replaces the update step of clustering.train (Retrieval.py:18). x_raw is the packed raw
+ * plane [n, kp]; assign i64[n] in [0, k). Writes centroids f32[k, d] (row stride d) as the
+ * mean of the assigned rows (fp64 accumulation in point order, rounded to fp32, times
+ * 1.0f/count like faiss) and hassign f32[k] = counts. Empty clusters keep zeros. */
+size_t nrb_kmeans_update_workspace(int64_t n, int32_t k);
+int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32_t kp,
+                      const int64_t* assign, int32_t k, float* centroids, float* hassign,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Host-side pieces of Clustering::train that faiss also runs on the host (tiny, sequential,
+ * RNG-driven): rand_perm (utils/random.cpp, std::mt19937, seed 1234 subsample / seed+1 init)
+ * and split_clusters (EPS = 1/1024, rng(1234)). Return value of split = nsplit. */
+int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed);
+int nrb_split_clusters_host(int32_t d, int32_t k, int64_t n, float* hassign, float* centroids);
+
+/* ---- K3: IVF lists (ArrayInvertedLists + search_preassigned / IVFFlatScanner) ------------- */
+/* Stable counting sort of rows by list id. Replaces the 300 boolean masks at Retrieval.py:23
+ * and IndexIVF::add_core. assign i64[n] in [0, nlist); writes offsets i32[nlist+1] and
+ * order i32[n]: packed position p holds source row order[p]; within a list, source order. */
+size_t nrb_ivf_build_lists_workspace(int64_t n, int32_t nlist);
+int nrb_ivf_build_lists(const int64_t* assign, int64_t n, int32_t nlist, int32_t* offsets,
+                        int32_t* order, void* workspace, size_t workspace_bytes, void* stream);
+/* Scans, for each query, the nprobe lists named by coarse i64[nq, nprobe] (best first; -1 =
+ * none) and keeps the top k by `metric`. `lists` is the list-contiguous packed matrix, ids
+ * i64[lists->n] the external id of each packed row. Replaces Retrieval.py:32-34 in its
+ * IndexIVFFlat form (north_star); results as nrb_search_flat. max_list_len = longest list
+ * (host-known since add()). The (query, list) pairs are regrouped list-major on the device so
+ * that every list is read once per 128 probing queries, not once per query. */
+size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k, int32_t kp, int32_t nlist,
+                                int32_t max_list_len);
+int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* offsets,
+                   int32_t nlist, int32_t max_list_len, const int64_t* ids, const int64_t* coarse,
+                   int32_t nprobe, int32_t metric, int32_t k, float* D, int64_t* I,
+                   void* workspace, size_t workspace_bytes, int32_t path, void* stream);
+
+/* ---- K4: k-way merge of per-shard results ------------------------------------------------- */
+/* Dp f32[nparts, nq, k], Ip i64[nparts, nq, k] (each best-first, -1 padded) -> global top-k.
+ * Sits after the NCCL all-gather of the catalog-sharded search (north_star item 4). */
+int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts, int64_t nq, int32_t k,
+                   int32_t metric, float* D, int64_t* I, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRB200_H */

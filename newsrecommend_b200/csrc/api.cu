@@ -1,0 +1,449 @@
+// extern "C" entry points of libnrb200 (declared in include/nrb200.h) that orchestrate several
+// kernels: exact flat top-k and the IVF list scan. Also error plumbing and the host-side RNG
+// pieces of k-means.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace nrb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+int sm_count() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+static int require_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libnrb200 has no CPU fallback");
+        return NRB_ERR_NO_DEVICE;
+    }
+    if (!tc_available()) {
+        set_error("current device is not sm_100: libnrb200 is built for B200 (sm_100a) only");
+        return NRB_ERR_NO_DEVICE;
+    }
+    return NRB_OK;
+}
+
+// Bump allocator over the caller's workspace.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base((char*)p) {}
+    template <typename T>
+    T* take(size_t count) {
+        T* r = (T*)(base ? base + off : nullptr);
+        off += align_up(count * sizeof(T), 256);
+        return r;
+    }
+};
+
+// ------------------------------------------------------------------------------ flat plan
+struct FlatPlan {
+    int nqt, nsplit, chunk_rows, n_units, grid;
+};
+
+static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
+    FlatPlan p;
+    const int sms = sm_count() * (path == NRB_PATH_SIMT ? 2 : 1);
+    p.nqt = (int)((nq + UNIT_ROWS - 1) / UNIT_ROWS);
+    if (p.nqt < 1) p.nqt = 1;
+    const int tile = 256;
+    int nbt = (int)((nb + tile - 1) / tile);
+    if (nbt < 1) nbt = 1;
+    int max_split = 8192 / k;
+    if (max_split > 64) max_split = 64;
+    if (max_split > nbt) max_split = nbt;
+    if (max_split < 1) max_split = 1;
+    int best = 1;
+    double best_eff = 0;
+    for (int s = 1; s <= max_split; s++) {
+        const double units = (double)p.nqt * s;
+        const double waves = (double)(((int64_t)p.nqt * s + sms - 1) / sms);
+        const double eff = units / (waves * sms);
+        if (eff > best_eff + 0.02) {
+            best_eff = eff;
+            best = s;
+        }
+    }
+    const int tiles_per = (nbt + best - 1) / best;
+    p.chunk_rows = tiles_per * tile;
+    p.nsplit = (nbt + tiles_per - 1) / tiles_per;
+    p.n_units = p.nqt * p.nsplit;
+    p.grid = path == NRB_PATH_SIMT ? simt_grid(p.n_units) : tc_grid(p.n_units);
+    return p;
+}
+
+struct FlatWs {
+    Unit* units;
+    int* n_units;
+    int* src;
+    float* part_key;
+    int* part_idx;
+    void* scratch;
+    size_t scratch_bytes;
+    size_t total;
+};
+
+static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int path) {
+    Carver c(ws);
+    FlatWs w;
+    w.units = c.take<Unit>(p.n_units);
+    w.n_units = c.take<int>(1);
+    w.src = c.take<int>((size_t)nq * p.nsplit);
+    w.part_key = c.take<float>((size_t)p.n_units * UNIT_ROWS * k);
+    w.part_idx = c.take<int>((size_t)p.n_units * UNIT_ROWS * k);
+    w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(p.grid) : tc_scratch_bytes(p.grid);
+    w.scratch = c.take<char>(w.scratch_bytes);
+    w.total = c.off;
+    return w;
+}
+
+static int resolve_path(int path) { return path == NRB_PATH_SIMT ? NRB_PATH_SIMT : NRB_PATH_TC; }
+
+// ------------------------------------------------------------------------------ IVF grouping
+// Single block: per list, the number of (query, list) pairs m_l, query tiles, item-run splits
+// and the first unit index; writes the unit list.
+__global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __restrict__ l_off, int nlist,
+                                int chunk, int* __restrict__ ubase, int* __restrict__ nsl,
+                                int* __restrict__ n_units_out, Unit* __restrict__ units, int max_units) {
+    extern __shared__ int cnt[];  // nlist + 1
+    for (int l = threadIdx.x; l < nlist; l += blockDim.x) {
+        const int m = p_off[l + 1] - p_off[l];
+        const int len = l_off[l + 1] - l_off[l];
+        const int tiles = (m + UNIT_ROWS - 1) / UNIT_ROWS;
+        const int ns = (m > 0 && len > 0) ? (len + chunk - 1) / chunk : 0;
+        nsl[l] = ns;
+        cnt[l] = tiles * ns;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < nlist; l++) {
+            const int t = cnt[l];
+            cnt[l] = run;
+            run += t;
+        }
+        cnt[nlist] = run;
+        *n_units_out = run < max_units ? run : max_units;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l <= nlist; l += blockDim.x) ubase[l] = cnt[l];
+    for (int l = threadIdx.x; l < nlist; l += blockDim.x) {
+        const int m = p_off[l + 1] - p_off[l];
+        const int len = l_off[l + 1] - l_off[l];
+        const int ns = nsl[l];
+        if (ns == 0) continue;
+        const int tiles = (m + UNIT_ROWS - 1) / UNIT_ROWS;
+        int u = cnt[l];
+        for (int t = 0; t < tiles; t++)
+            for (int s = 0; s < ns; s++, u++) {
+                if (u >= max_units) continue;
+                Unit un;
+                un.a_row0 = p_off[l] + t * UNIT_ROWS;
+                un.a_rows = min(UNIT_ROWS, m - t * UNIT_ROWS);
+                un.b_row0 = l_off[l] + s * chunk;
+                un.b_rows = min(chunk, len - s * chunk);
+                units[u] = un;
+            }
+    }
+}
+
+// src[(q*nprobe + j)*maxsplit + s] = partial row of pair (q, j) in split s, or -1.
+__global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __restrict__ pos_of,
+                               const int* __restrict__ p_off, const int* __restrict__ ubase,
+                               const int* __restrict__ nsl, int nlist, int64_t npairs, int maxsplit,
+                               int* __restrict__ src) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < npairs;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = pos_of[e];
+        const int64_t l = coarse[e];
+        int ns = 0, first = 0;
+        if (pos >= 0 && l >= 0 && l < nlist) {
+            ns = nsl[l];
+            const int i = pos - p_off[l];
+            first = (ubase[l] + (i / UNIT_ROWS) * ns) * UNIT_ROWS + (i % UNIT_ROWS);
+        }
+        for (int s = 0; s < maxsplit; s++)
+            src[e * maxsplit + s] = (s < ns) ? first + s * UNIT_ROWS : -1;
+    }
+}
+
+constexpr int IVF_CHUNK = 2048;  // item rows per unit inside one list
+
+struct IvfPlan {
+    int64_t npairs;
+    int maxsplit, max_units, grid;
+};
+
+static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int path) {
+    IvfPlan p;
+    p.npairs = nq * nprobe;
+    p.maxsplit = (max_list_len + IVF_CHUNK - 1) / IVF_CHUNK;
+    if (p.maxsplit < 1) p.maxsplit = 1;
+    int64_t mu = (p.npairs / UNIT_ROWS + nlist) * p.maxsplit;
+    p.max_units = (int)mu;
+    p.grid = path == NRB_PATH_SIMT ? simt_grid(p.max_units) : tc_grid(p.max_units);
+    return p;
+}
+
+struct IvfWs {
+    void* cs;
+    size_t cs_bytes;
+    int *p_off, *order, *pos_of, *ubase, *nsl, *n_units, *src;
+    Unit* units;
+    float *g_raw, *g_hi, *g_lo, *g_norms, *part_key;
+    int* part_idx;
+    void* scratch;
+    size_t scratch_bytes, total;
+};
+
+static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int path) {
+    Carver c(ws);
+    IvfWs w;
+    w.cs_bytes = counting_sort_ws(p.npairs, nlist);
+    w.cs = c.take<char>(w.cs_bytes);
+    w.p_off = c.take<int>(nlist + 2);
+    w.order = c.take<int>(p.npairs);
+    w.pos_of = c.take<int>(p.npairs);
+    w.ubase = c.take<int>(nlist + 1);
+    w.nsl = c.take<int>(nlist);
+    w.n_units = c.take<int>(1);
+    w.src = c.take<int>((size_t)p.npairs * p.maxsplit);
+    w.units = c.take<Unit>(p.max_units);
+    const size_t plane = (size_t)(p.npairs + UNIT_ROWS) * kp;
+    if (path == NRB_PATH_SIMT) {
+        w.g_raw = c.take<float>(plane);
+        w.g_hi = w.g_lo = nullptr;
+    } else {
+        w.g_raw = nullptr;
+        w.g_hi = c.take<float>(plane);
+        w.g_lo = c.take<float>(plane);
+    }
+    w.g_norms = c.take<float>(p.npairs + UNIT_ROWS);
+    w.part_key = c.take<float>((size_t)p.max_units * UNIT_ROWS * k);
+    w.part_idx = c.take<int>((size_t)p.max_units * UNIT_ROWS * k);
+    w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(p.grid) : tc_scratch_bytes(p.grid);
+    w.scratch = c.take<char>(w.scratch_bytes);
+    w.total = c.off;
+    return w;
+}
+
+}  // namespace nrb
+
+using namespace nrb;
+
+extern "C" int nrb_version(void) { return 100; }
+
+extern "C" int nrb_last_error(char* buf, int buflen) {
+    if (!buf || buflen <= 0) return NRB_ERR_INVALID;
+    strncpy(buf, g_err, buflen - 1);
+    buf[buflen - 1] = 0;
+    return NRB_OK;
+}
+
+extern "C" int nrb_device_info(int* sms, int* cc_major, int* cc_minor) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device");
+        return NRB_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    NRB_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    NRB_CUDA_CHECK(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return NRB_OK;
+}
+
+extern "C" int64_t nrb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp) {
+    (void)kp;
+    if (nq <= 0 || k <= 0 || k > NRB_MAX_K) return 256;
+    // the SIMT plan uses the wider grid; take the larger of both so `path` can be chosen per call
+    FlatPlan p1 = plan_flat(nq, nb, k, NRB_PATH_TC), p2 = plan_flat(nq, nb, k, NRB_PATH_SIMT);
+    size_t a = carve_flat(nullptr, p1, nq, k, NRB_PATH_TC).total;
+    size_t b = carve_flat(nullptr, p2, nq, k, NRB_PATH_SIMT).total;
+    return (a > b ? a : b) + 256;
+}
+
+extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
+                               int64_t id_base, float* D, int64_t* I, void* workspace,
+                               size_t workspace_bytes, int32_t path, void* stream) {
+    NRB_REQUIRE(q && b && D && I, "search_flat: null argument");
+    NRB_REQUIRE(metric == NRB_METRIC_INNER_PRODUCT || metric == NRB_METRIC_L2, "search_flat: bad metric %d", metric);
+    NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "search_flat: k=%d out of range [1,%d]", k, NRB_MAX_K);
+    NRB_REQUIRE(q->d == b->d && q->kp == b->kp, "search_flat: dimension mismatch (%d/%d vs %d/%d)", q->d, q->kp, b->d, b->kp);
+    NRB_REQUIRE(q->n >= 0 && b->n >= 0 && b->n < (1LL << 31) - 4096 && q->n < (1LL << 31), "search_flat: sizes out of range");
+    if (q->n == 0) return NRB_OK;
+    int rc = require_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    path = resolve_path(path);
+    const FlatPlan p = plan_flat(q->n, b->n, k, path);
+    const FlatWs w = carve_flat(workspace, p, q->n, k, path);
+    if (!workspace || workspace_bytes < w.total) {
+        set_error("search_flat: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return NRB_ERR_WORKSPACE;
+    }
+    if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.nsplit, p.chunk_rows, st))) return rc;
+    if (path == NRB_PATH_SIMT)
+        rc = launch_topk_simt_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    else
+        rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    if (rc) return rc;
+    return launch_select(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, metric, nullptr, id_base, D, I, st);
+}
+
+extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k, int32_t kp,
+                                           int32_t nlist, int32_t max_list_len) {
+    if (nq <= 0 || nprobe <= 0 || k <= 0) return 256;
+    IvfPlan p1 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_TC);
+    IvfPlan p2 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_SIMT);
+    size_t a = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC).total;
+    size_t b = carve_ivf(nullptr, p2, nlist, k, kp, NRB_PATH_SIMT).total;
+    return (a > b ? a : b) + 256;
+}
+
+extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* offsets,
+                              int32_t nlist, int32_t max_list_len, const int64_t* ids,
+                              const int64_t* coarse, int32_t nprobe, int32_t metric, int32_t k,
+                              float* D, int64_t* I, void* workspace, size_t workspace_bytes,
+                              int32_t path, void* stream) {
+    NRB_REQUIRE(q && lists && offsets && ids && coarse && D && I, "ivf_search: null argument");
+    NRB_REQUIRE(metric == NRB_METRIC_INNER_PRODUCT || metric == NRB_METRIC_L2, "ivf_search: bad metric %d", metric);
+    NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "ivf_search: k=%d out of range [1,%d]", k, NRB_MAX_K);
+    NRB_REQUIRE(nprobe >= 1 && nlist >= 1 && nlist <= 8192, "ivf_search: bad nprobe/nlist");
+    NRB_REQUIRE(q->d == lists->d && q->kp == lists->kp, "ivf_search: dimension mismatch");
+    NRB_REQUIRE(q->n * (int64_t)nprobe < (1LL << 31) - 4096 && lists->n < (1LL << 31) - 4096, "ivf_search: sizes out of range");
+    if (q->n == 0) return NRB_OK;
+    int rc = require_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    path = resolve_path(path);
+    const IvfPlan p = plan_ivf(q->n, nprobe, nlist, max_list_len, path);
+    NRB_REQUIRE((int64_t)nprobe * p.maxsplit * k <= 16384, "ivf_search: nprobe*splits*k too large");
+    const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path);
+    if (!workspace || workspace_bytes < w.total) {
+        set_error("ivf_search: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return NRB_ERR_WORKSPACE;
+    }
+    // 1. group (query, list) pairs by list (stable): p_off, order (position -> pair), pos_of
+    NRB_CUDA_CHECK(cudaMemsetAsync(w.order, 0, (size_t)p.npairs * sizeof(int), st));
+    if ((rc = launch_counting_sort_i64(coarse, p.npairs, nlist, w.p_off, w.order, w.pos_of, w.cs, w.cs_bytes, st))) return rc;
+    // 2. units + src table, all on the device
+    const size_t sh = (size_t)(nlist + 1) * sizeof(int);
+    ivf_plan_kernel<<<1, 512, sh, st>>>(w.p_off, offsets, nlist, IVF_CHUNK, w.ubase, w.nsl, w.n_units, w.units, p.max_units);
+    NRB_LAUNCH_CHECK();
+    {
+        int64_t blocks = (p.npairs + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        ivf_src_kernel<<<(unsigned)blocks, 256, 0, st>>>(coarse, w.pos_of, w.p_off, w.ubase, w.nsl, nlist, p.npairs, p.maxsplit, w.src);
+        NRB_LAUNCH_CHECK();
+    }
+    // 3. query rows in group order
+    nrb_matrix g;
+    g.n = p.npairs;
+    g.d = q->d;
+    g.kp = q->kp;
+    g.raw = w.g_raw;
+    g.hi = w.g_hi;
+    g.lo = w.g_lo;
+    g.norms = nullptr;
+    if (path == NRB_PATH_SIMT) {
+        NRB_REQUIRE(q->raw, "ivf_search: raw plane required");
+        if ((rc = launch_gather_rows(q->raw, q->kp, w.order, nprobe, p.npairs, w.g_raw, st))) return rc;
+    } else {
+        NRB_REQUIRE(q->hi && q->lo, "ivf_search: hi/lo planes required");
+        if ((rc = launch_gather_rows(q->hi, q->kp, w.order, nprobe, p.npairs, w.g_hi, st))) return rc;
+        if ((rc = launch_gather_rows(q->lo, q->kp, w.order, nprobe, p.npairs, w.g_lo, st))) return rc;
+    }
+    if (metric == NRB_METRIC_L2) {
+        NRB_REQUIRE(q->norms && lists->norms, "ivf_search: norms required for L2");
+        if ((rc = launch_gather_scalar(q->norms, w.order, nprobe, p.npairs, w.g_norms, st))) return rc;
+        g.norms = w.g_norms;
+    }
+    // 4. distance + selection over the units, 5. merge per query
+    if (path == NRB_PATH_SIMT)
+        rc = launch_topk_simt_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    else
+        rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    if (rc) return rc;
+    return launch_select(w.part_key, w.part_idx, w.src, nprobe * p.maxsplit, q->n, k, metric, ids, 0, D, I, st);
+}
+
+extern "C" int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed) {
+    NRB_REQUIRE(perm && n >= 0, "rand_perm: bad arguments");
+    std::mt19937 mt((unsigned)seed);
+    for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+    for (int64_t i = 0; i + 1 < n; i++) {
+        const int64_t i2 = i + (int64_t)(mt() % (uint32_t)(n - i));
+        std::swap(perm[i], perm[i2]);
+    }
+    return NRB_OK;
+}
+
+extern "C" int nrb_split_clusters_host(int32_t d, int32_t k, int64_t n, float* hassign, float* centroids) {
+    NRB_REQUIRE(hassign && centroids && d > 0 && k > 0 && n > k, "split_clusters: bad arguments");
+    const double EPS = 1 / 1024.;
+    std::mt19937 mt(1234);
+    int nsplit = 0;
+    for (int ci = 0; ci < k; ci++) {
+        if (hassign[ci] != 0) continue;
+        int cj = 0;
+        for (int guard = 0;; cj = (cj + 1) % k) {
+            const float p = (hassign[cj] - 1.0) / (float)(n - k);
+            const float r = mt() / float(mt.max());
+            if (r < p) break;
+            if (++guard > 100000000) {
+                set_error("split_clusters: no cluster to split");
+                return NRB_ERR_INVALID;
+            }
+        }
+        float* a = centroids + (size_t)ci * d;
+        float* b = centroids + (size_t)cj * d;
+        memcpy(a, b, sizeof(float) * d);
+        for (int j = 0; j < d; j++) {
+            if (j % 2 == 0) {
+                a[j] *= 1 + EPS;
+                b[j] *= 1 - EPS;
+            } else {
+                a[j] *= 1 - EPS;
+                b[j] *= 1 + EPS;
+            }
+        }
+        hassign[ci] = hassign[cj] / 2;
+        hassign[cj] -= hassign[ci];
+        nsplit++;
+    }
+    return nsplit;
+}

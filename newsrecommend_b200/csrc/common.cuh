@@ -1,0 +1,139 @@
+// Shared helpers for libnrb200: error plumbing, ordered keys, and the warp-cooperative
+// candidate-buffer prune used by every selection epilogue.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nrb200.h"
+
+namespace nrb {
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define NRB_CUDA_CHECK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            nrb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                           cudaGetErrorString(_e));                                       \
+            return NRB_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define NRB_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        nrb::count_launch();                                                              \
+        NRB_CUDA_CHECK(cudaGetLastError());                                               \
+    } while (0)
+
+#define NRB_REQUIRE(cond, ...)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            nrb::set_error(__VA_ARGS__);                                                  \
+            return NRB_ERR_INVALID;                                                       \
+        }                                                                                 \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- selection primitives
+// All selection works on "keys" where LARGER IS BETTER: key = score for inner product and
+// key = -distance for L2. A candidate is the pair (key, idx); idx is a 32-bit row index
+// (>= 0). Candidates are ordered by (key descending, idx ascending), so exact ties resolve to
+// the lowest id the way faiss's k=1 strict-compare heap does.
+constexpr int CAND_CAP = 256;  // per-row candidate buffer capacity (entries)
+constexpr float NEG_INF = -__builtin_huge_valf();
+
+__device__ __forceinline__ uint64_t pack_cand(float key, int idx) {
+    uint32_t u = __float_as_uint(key);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((uint64_t)u << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)idx);
+}
+__device__ __forceinline__ float cand_key(uint64_t c) {
+    uint32_t u = (uint32_t)(c >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ int cand_idx(uint64_t c) {
+    return (int)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFu));
+}
+// The empty candidate: (-inf, idx -1) packs below every real candidate.
+__device__ __forceinline__ uint64_t empty_cand() { return pack_cand(NEG_INF, -1); }
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// Bitonic sort (descending) of 32*R packed candidates held striped across a warp:
+// element e = i*32 + lane lives in c[i].
+template <int R>
+__device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * R; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j >= 1; j >>= 1) {
+            if (j >= 32) {
+                const int jj = j >> 5;
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    if ((i & jj) == 0) {
+                        const bool desc = (((i * 32) & k2) == 0);  // k2 >= 64 here
+                        uint64_t a = c[i], b = c[i | jj];
+                        uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+                        c[i] = desc ? mx : mn;
+                        c[i | jj] = desc ? mn : mx;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const int e = i * 32 + lane;
+                    const bool desc = ((e & k2) == 0);
+                    const bool lower = ((lane & j) == 0);
+                    uint64_t a = c[i];
+                    uint64_t b = shfl_xor_u64(a, j);
+                    const bool take_max = (lower == desc);
+                    c[i] = take_max ? (a > b ? a : b) : (a > b ? b : a);
+                }
+            }
+        }
+    }
+}
+
+// Warp-cooperative prune of one row's candidate buffer: keeps the best `k` of the first `n`
+// entries of (bk, bi), writes them best-first to (ok, oi) (which may alias bk/bi), pads
+// [min(n,k), k) with the empty candidate, and returns the new threshold = key of the k-th best
+// (NEG_INF while fewer than k candidates exist). All 32 lanes must call with identical args.
+__device__ __forceinline__ float warp_prune_row(const float* bk, const int* bi, int n, int k,
+                                                float* ok, int* oi, int lane) {
+    constexpr int R = CAND_CAP / 32;
+    uint64_t c[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const int e = i * 32 + lane;
+        c[i] = (e < n) ? pack_cand(bk[e], bi[e]) : empty_cand();
+    }
+    __syncwarp();
+    warp_bitonic_desc<R>(c, lane);
+    float kth = NEG_INF;
+    const int kl = (k - 1) & 31, ki = (k - 1) >> 5;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const int e = i * 32 + lane;
+        if (e < k) {
+            ok[e] = cand_key(c[i]);
+            oi[e] = cand_idx(c[i]);
+        }
+        if (i == ki) kth = cand_key(c[i]);
+    }
+    kth = __shfl_sync(0xffffffffu, kth, kl);
+    __syncwarp();
+    return kth;  // NEG_INF if the k-th slot is an empty candidate
+}
+
+}  // namespace nrb

@@ -1,0 +1,57 @@
+// Internal C++ interfaces between the translation units of libnrb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nrb200.h"
+
+namespace nrb {
+
+// One unit of selection work: rows [a_row0, a_row0 + a_rows) of the query-side matrix against
+// rows [b_row0, b_row0 + b_rows) of the item-side matrix. a_rows <= 128. Unit u writes its
+// partial result (best-first top-k per row, padded) to partial rows [u*128, u*128 + 128).
+struct Unit {
+    int a_row0;
+    int a_rows;
+    int b_row0;
+    int b_rows;
+};
+
+constexpr int UNIT_ROWS = 128;
+
+// ---- topk_tc.cu: tcgen05 3xTF32 distance + selection. n_units lives in device memory so that
+// unit lists built on the device (IVF grouping) need no host round trip; `grid` is the host's
+// launch width (<= number of SMs).
+int tc_available();  // 1 when the current device is sm_100
+size_t tc_scratch_bytes(int grid);
+int tc_grid(int n_units_upper);
+int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
+                       const int* n_units_dev, int grid, int metric, int k, float* part_key,
+                       int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+// ---- topk_simt.cu: fp32 CUDA-core distance + selection over the same Unit list
+size_t simt_scratch_bytes(int grid);
+int simt_grid(int n_units_upper);
+int launch_topk_simt_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
+                         const int* n_units_dev, int grid, int metric, int k, float* part_key,
+                         int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+// ---- kernels_misc.cu
+// src[q*S + s] = partial row index (or -1). id_map (optional) translates idx -> external id;
+// otherwise id = idx + id_base.
+int launch_select(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
+                  int k, int metric, const int64_t* id_map, int64_t id_base, float* D, int64_t* I,
+                  cudaStream_t st);
+int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
+                           int nsplit, int chunk_rows, cudaStream_t st);
+size_t counting_sort_ws(int64_t n, int nb);
+int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets, int* order,
+                             int* pos_of, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gather_rows(const float* src, int width, const int32_t* idx, int div, int64_t n,
+                       float* dst, cudaStream_t st);
+int launch_gather_scalar(const float* src, const int32_t* idx, int div, int64_t n, float* dst,
+                         cudaStream_t st);
+
+int sm_count();
+
+}  // namespace nrb

@@ -1,0 +1,564 @@
+// HBM-bound helper kernels: pack/split (K0), row gather, L2 normalise, stable counting sort by
+// list (K3 layout / K1b grouping), segmented centroid update (K1b), and the final select /
+// k-way merge (K4).
+#include <cfloat>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace nrb {
+
+// ------------------------------------------------------------------------------------ K0 pack
+// One warp per row. x[n, d] (stride ldx) -> raw/hi/lo [n, kp] and norms[n].
+// Reference: replaces the numpy astype/ascontiguousarray at Retrieval.py:8,17,31.
+__global__ void pack_rows_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                 int kp, float* __restrict__ raw, float* __restrict__ hi,
+                                 float* __restrict__ lo, float* __restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp0; row < n; row += nwarps) {
+        const float* xr = x + row * ldx;
+        float acc = 0.f;
+        for (int c = lane; c < kp; c += 32) {
+            float v = (c < d) ? xr[c] : 0.f;
+            acc = fmaf(v, v, acc);
+            const int64_t o = row * kp + c;
+            if (raw) raw[o] = v;
+            if (hi || lo) {
+                uint32_t hb, lb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+                float h = __uint_as_float(hb);
+                float l = v - h;  // exact in fp32
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(l));
+                if (hi) hi[o] = h;
+                if (lo) lo[o] = __uint_as_float(lb);
+            }
+        }
+        if (norms) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) norms[row] = acc;
+        }
+    }
+}
+
+// dst[i, :] = src[idx[i] / div, :], rows of `width` floats (width % 4 == 0), float4 lanes.
+__global__ void gather_rows_kernel(const float4* __restrict__ src, int w4,
+                                   const int32_t* __restrict__ idx, int div, int64_t n,
+                                   float4* __restrict__ dst) {
+    const int64_t total = n * w4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / w4;
+        const int c = (int)(t - i * w4);
+        const int64_t s = idx[i] / div;
+        dst[t] = __ldg(src + s * w4 + c);
+    }
+}
+
+__global__ void gather_scalar_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                     int div, int64_t n, float* __restrict__ dst) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (int64_t)gridDim.x * blockDim.x)
+        dst[t] = src[idx[t] / div];
+}
+
+__global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ idx,
+                                  int64_t n, int64_t* __restrict__ dst) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (int64_t)gridDim.x * blockDim.x)
+        dst[t] = src[idx[t]];
+}
+
+// faiss.normalize_L2: warp per row, in place.
+__global__ void normalize_l2_kernel(float* __restrict__ x, int64_t n, int d, int64_t ldx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp0; row < n; row += nwarps) {
+        float* xr = x + row * ldx;
+        float acc = 0.f;
+        for (int c = lane; c < d; c += 32) acc = fmaf(xr[c], xr[c], acc);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (acc > 0.f) {
+            const float inv = 1.0f / sqrtf(acc);
+            for (int c = lane; c < d; c += 32) xr[c] *= inv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- stable counting sort
+// Sorts items 0..n by key[i] in [0, nb) (keys outside the range, e.g. -1, go to bucket nb and
+// are dropped from `order`) keeping source order inside a bucket. Three kernels:
+//   hist: per-chunk bucket counts; scan: bucket offsets + per-chunk bases; scatter.
+constexpr int CS_CHUNK = 2048;
+constexpr int CS_THREADS = 256;
+
+template <typename KeyT>
+__global__ void cs_hist_kernel(const KeyT* __restrict__ key, int64_t n, int nb,
+                               int* __restrict__ chunk_hist /*[nchunks, nb+1]*/) {
+    extern __shared__ int sh[];
+    const int nb1 = nb + 1;
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    const int64_t i0 = (int64_t)blockIdx.x * CS_CHUNK;
+    for (int t = threadIdx.x; t < CS_CHUNK; t += blockDim.x) {
+        const int64_t i = i0 + t;
+        if (i < n) {
+            int64_t kk = (int64_t)key[i];
+            int b = (kk >= 0 && kk < nb) ? (int)kk : nb;
+            atomicAdd(&sh[b], 1);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x)
+        chunk_hist[(int64_t)blockIdx.x * nb1 + b] = sh[b];
+}
+
+// Single block. offsets[nb+1] (exclusive scan of bucket totals over real buckets; offsets[nb] =
+// number of kept items) and chunk_hist rewritten in place to per-chunk bases.
+__global__ void cs_scan_kernel(int* __restrict__ chunk_hist, int nchunks, int nb,
+                               int* __restrict__ offsets) {
+    extern __shared__ int tot[];  // nb + 2
+    const int nb1 = nb + 1;
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) {
+        int s = 0;
+        for (int c = 0; c < nchunks; c++) s += chunk_hist[(int64_t)c * nb1 + b];
+        tot[b] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nb1; b++) {
+            int t = tot[b];
+            tot[b] = run;
+            run += t;
+        }
+        tot[nb1] = run;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= nb; b += blockDim.x) offsets[b] = tot[b];
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) {
+        int run = tot[b];
+        for (int c = 0; c < nchunks; c++) {
+            const int64_t o = (int64_t)c * nb1 + b;
+            int t = chunk_hist[o];
+            chunk_hist[o] = run;
+            run += t;
+        }
+    }
+}
+
+template <typename KeyT>
+__global__ void cs_scatter_kernel(const KeyT* __restrict__ key, int64_t n, int nb,
+                                  const int* __restrict__ chunk_base, int* __restrict__ order,
+                                  int* __restrict__ pos_of /*optional: item -> position*/) {
+    extern __shared__ int run[];  // nb + 1 running positions
+    const int nb1 = nb + 1;
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x)
+        run[b] = chunk_base[(int64_t)blockIdx.x * nb1 + b];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * CS_CHUNK;
+    for (int r0 = 0; r0 < CS_CHUNK; r0 += blockDim.x) {
+        const int64_t i = i0 + r0 + threadIdx.x;
+        int b = -1;
+        if (i < n) {
+            int64_t kk = (int64_t)key[i];
+            b = (kk >= 0 && kk < nb) ? (int)kk : nb;
+        }
+        // rank among same-bucket lanes of this warp (lower lanes first)
+        unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        // warps take turns so that positions follow source order
+        for (int w = 0; w < nwarps; w++) {
+            if (w == warp && b >= 0 && lane == leader) {
+                base = run[b];
+                run[b] = base + __popc(peers);
+            }
+            __syncthreads();
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (b >= 0) {
+            const int p = base + rank;
+            if (b < nb) order[p] = (int)i;
+            if (pos_of) pos_of[i] = (b < nb) ? p : -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- K1b centroid update
+// Block per centroid. Threads = (kp/4 float4 columns) x RS row slices; each thread sums its
+// slice's rows in source order in fp64; slices are combined in a fixed order, so the result is
+// deterministic. mean = float(sum) * (1.0f / count)  (Clustering.cpp compute_centroids).
+template <int RS>
+__global__ void kmeans_update_kernel(const float* __restrict__ x_raw, int kp, int d,
+                                     const int* __restrict__ offsets,
+                                     const int* __restrict__ order, float* __restrict__ centroids,
+                                     float* __restrict__ hassign) {
+    extern __shared__ double part[];  // [RS][kp]
+    const int c = blockIdx.x;
+    const int w4 = kp >> 2;
+    const int col4 = threadIdx.x % w4;
+    const int slice = threadIdx.x / w4;
+    const int r0 = offsets[c], r1 = offsets[c + 1];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (slice < RS) {
+        for (int r = r0 + slice; r < r1; r += RS) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x_raw + (int64_t)order[r] * kp) + col4);
+            a0 += v.x;
+            a1 += v.y;
+            a2 += v.z;
+            a3 += v.w;
+        }
+        double* p = part + (int64_t)slice * kp + col4 * 4;
+        p[0] = a0;
+        p[1] = a1;
+        p[2] = a2;
+        p[3] = a3;
+    }
+    __syncthreads();
+    const int cnt = r1 - r0;
+    if (threadIdx.x == 0) hassign[c] = (float)cnt;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < RS; q++) s += part[(int64_t)q * kp + j];
+        float m = 0.f;
+        if (cnt > 0) m = (float)s * (1.0f / (float)cnt);
+        centroids[(int64_t)c * d + j] = m;
+    }
+}
+
+// ------------------------------------------------------------------- select / merge (K4)
+// Block per query. Gathers S partial rows of k best-first candidates, sorts (key desc, idx
+// asc) with a shared-memory bitonic network and writes the k best.
+__global__ void select_kernel(const float* __restrict__ part_key, const int* __restrict__ part_idx,
+                              const int* __restrict__ src, int S, int k, int P /*pow2 >= S*k*/,
+                              int metric, const int64_t* __restrict__ id_map, int64_t id_base,
+                              float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ uint64_t sc[];
+    const int64_t q = blockIdx.x;
+    const int total = S * k;
+    for (int e = threadIdx.x; e < P; e += blockDim.x) {
+        uint64_t c = empty_cand();
+        if (e < total) {
+            const int s = e / k, j = e - s * k;
+            const int prow = src[q * S + s];
+            if (prow >= 0) {
+                const int64_t o = (int64_t)prow * k + j;
+                const int idx = part_idx[o];
+                if (idx >= 0) c = pack_cand(part_key[o], idx);
+            }
+        }
+        sc[e] = c;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j >= 1; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int e = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower element of the pair
+                const int p = e | j;
+                const bool desc = ((e & k2) == 0);
+                const uint64_t a = sc[e], b = sc[p];
+                if ((a < b) == desc) {
+                    sc[e] = b;
+                    sc[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint64_t c = sc[j];
+        const int idx = cand_idx(c);
+        float key = cand_key(c);
+        int64_t id;
+        float dv;
+        if (idx < 0) {
+            id = -1;
+            dv = (metric == NRB_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+        } else {
+            id = id_map ? id_map[idx] : (int64_t)idx + id_base;
+            dv = (metric == NRB_METRIC_L2) ? -key : key;
+        }
+        D[q * k + j] = dv;
+        I[q * k + j] = id;
+    }
+}
+
+// k-way merge of per-shard (D, I): same network, keys from D, 64-bit ids carried by position.
+__global__ void merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip,
+                             int nparts, int64_t nq, int k, int P, int metric,
+                             float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ uint64_t sc[];
+    const int64_t q = blockIdx.x;
+    const int total = nparts * k;
+    for (int e = threadIdx.x; e < P; e += blockDim.x) {
+        uint64_t c = empty_cand();
+        if (e < total) {
+            const int s = e / k, j = e - s * k;
+            const int64_t o = ((int64_t)s * nq + q) * k + j;
+            if (Ip[o] >= 0) {
+                const float d = Dp[o];
+                // idx slot carries the position e; ties between shards resolve by shard order,
+                // which is ascending id order for a row-sharded catalog.
+                c = pack_cand(metric == NRB_METRIC_L2 ? -d : d, e);
+            }
+        }
+        sc[e] = c;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j >= 1; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int e = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = e | j;
+                const bool desc = ((e & k2) == 0);
+                const uint64_t a = sc[e], b = sc[p];
+                if ((a < b) == desc) {
+                    sc[e] = b;
+                    sc[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint64_t c = sc[j];
+        const int e = cand_idx(c);
+        if (e < 0) {
+            I[q * k + j] = -1;
+            D[q * k + j] = (metric == NRB_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+        } else {
+            const int s = e / k, jj = e - s * k;
+            const int64_t o = ((int64_t)s * nq + q) * k + jj;
+            I[q * k + j] = Ip[o];
+            D[q * k + j] = Dp[o];
+        }
+    }
+}
+
+// Units + src table of the flat search: unit u = s*nqt + t covers query tile t and item chunk
+// s; concurrently resident CTAs (consecutive u) share the chunk, so its tiles stay in L2.
+__global__ void fill_flat_units_kernel(Unit* __restrict__ units, int* __restrict__ n_units_out,
+                                       int* __restrict__ src, int64_t nq, int64_t nb, int nqt,
+                                       int nsplit, int chunk_rows) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nunits = (int64_t)nqt * nsplit;
+    if (tid == 0) *n_units_out = (int)nunits;
+    if (tid < nunits) {
+        const int s = (int)(tid / nqt), t = (int)(tid % nqt);
+        Unit u;
+        u.a_row0 = t * UNIT_ROWS;
+        int64_t ar = nq - (int64_t)t * UNIT_ROWS;
+        u.a_rows = (int)(ar < UNIT_ROWS ? ar : UNIT_ROWS);
+        u.b_row0 = s * chunk_rows;
+        int64_t br = nb - (int64_t)s * chunk_rows;
+        u.b_rows = (int)(br < chunk_rows ? (br > 0 ? br : 0) : chunk_rows);
+        units[tid] = u;
+    }
+    const int64_t total = nq * nsplit;
+    for (int64_t e = tid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = e / nsplit;
+        const int s = (int)(e - q * nsplit);
+        src[e] = (int)(((int64_t)s * nqt + q / UNIT_ROWS) * UNIT_ROWS + q % UNIT_ROWS);
+    }
+}
+
+// ------------------------------------------------------------------- host launchers
+static int pow2_ge(int x) {
+    int p = 2;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+int launch_select(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
+                  int k, int metric, const int64_t* id_map, int64_t id_base, float* D, int64_t* I,
+                  cudaStream_t st) {
+    if (nq == 0) return NRB_OK;
+    const int P = pow2_ge(S * k);
+    NRB_REQUIRE(P <= 16384, "select: S*k = %d too large", S * k);
+    const size_t smem = (size_t)P * sizeof(uint64_t);
+    if (smem > 48 * 1024)
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(select_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = P / 2;
+    threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
+    select_kernel<<<(unsigned)nq, threads, smem, st>>>(part_key, part_idx, src, S, k, P, metric,
+                                                       id_map, id_base, D, I);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
+                           int nsplit, int chunk_rows, cudaStream_t st) {
+    const int64_t total = nq * nsplit;
+    int64_t nunits = (int64_t)nqt * nsplit;
+    int64_t work = total > nunits ? total : nunits;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < (nunits + 255) / 256) blocks = (int)((nunits + 255) / 256);
+    fill_flat_units_kernel<<<blocks, 256, 0, st>>>(units, n_units_out, src, nq, nb, nqt, nsplit, chunk_rows);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets, int* order,
+                             int* pos_of, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int nchunks = (int)((n + CS_CHUNK - 1) / CS_CHUNK);
+    const size_t need = (size_t)(nchunks > 0 ? nchunks : 1) * (nb + 1) * sizeof(int);
+    if (ws_bytes < need) {
+        set_error("counting sort: workspace %zu < %zu", ws_bytes, need);
+        return NRB_ERR_WORKSPACE;
+    }
+    int* chunk_hist = (int*)ws;
+    const size_t sh = (size_t)(nb + 2) * sizeof(int);
+    NRB_REQUIRE(sh <= 48 * 1024, "counting sort: too many buckets (%d)", nb);
+    if (nchunks > 0) {
+        cs_hist_kernel<int64_t><<<nchunks, CS_THREADS, sh, st>>>(key, n, nb, chunk_hist);
+        NRB_LAUNCH_CHECK();
+    }
+    cs_scan_kernel<<<1, 512, sh, st>>>(chunk_hist, nchunks, nb, offsets);
+    NRB_LAUNCH_CHECK();
+    if (nchunks > 0) {
+        cs_scatter_kernel<int64_t><<<nchunks, CS_THREADS, sh, st>>>(key, n, nb, chunk_hist, order, pos_of);
+        NRB_LAUNCH_CHECK();
+    }
+    return NRB_OK;
+}
+
+size_t counting_sort_ws(int64_t n, int nb) {
+    const int64_t nchunks = (n + CS_CHUNK - 1) / CS_CHUNK;
+    return align_up((size_t)(nchunks > 0 ? nchunks : 1) * (nb + 1) * sizeof(int), 256);
+}
+
+}  // namespace nrb
+
+using namespace nrb;
+
+extern "C" int nrb_pack_rows(const float* x, int64_t n, int32_t d, int64_t ldx, int32_t kp,
+                             float* raw, float* hi, float* lo, float* norms, void* stream) {
+    NRB_REQUIRE(n >= 0 && d > 0 && kp >= d && kp % 32 == 0 && ldx >= d,
+                "pack_rows: bad shape n=%lld d=%d kp=%d ldx=%lld", (long long)n, d, kp, (long long)ldx);
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, d, ldx, kp, raw, hi, lo, norms);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+namespace nrb {
+int launch_gather_rows(const float* src, int width, const int32_t* idx, int div, int64_t n,
+                       float* dst, cudaStream_t st) {
+    if (n == 0) return NRB_OK;
+    int64_t total = n * (width / 4);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float4*)src, width / 4, idx, div, n, (float4*)dst);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+int launch_gather_scalar(const float* src, const int32_t* idx, int div, int64_t n, float* dst,
+                         cudaStream_t st) {
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gather_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, idx, div, n, dst);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+}  // namespace nrb
+
+extern "C" int nrb_gather_rows(const float* src, int32_t width, const int32_t* idx, int64_t n,
+                               float* dst, void* stream) {
+    NRB_REQUIRE(width > 0 && width % 4 == 0 && n >= 0, "gather_rows: width %d must be a multiple of 4", width);
+    return launch_gather_rows(src, width, idx, 1, n, dst, (cudaStream_t)stream);
+}
+
+extern "C" int nrb_gather_i64(const int64_t* src, const int32_t* idx, int64_t n, int64_t* dst,
+                              void* stream) {
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gather_i64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+extern "C" int nrb_normalize_l2(float* x, int64_t n, int32_t d, int64_t ldx, void* stream) {
+    NRB_REQUIRE(n >= 0 && d > 0 && ldx >= d, "normalize_l2: bad shape");
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    normalize_l2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, d, ldx);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+extern "C" size_t nrb_ivf_build_lists_workspace(int64_t n, int32_t nlist) {
+    return counting_sort_ws(n, nlist);
+}
+
+extern "C" int nrb_ivf_build_lists(const int64_t* assign, int64_t n, int32_t nlist,
+                                   int32_t* offsets, int32_t* order, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    NRB_REQUIRE(n >= 0 && n < (1LL << 31) && nlist > 0, "ivf_build_lists: bad sizes");
+    return launch_counting_sort_i64(assign, n, nlist, offsets, order, nullptr, workspace,
+                                    workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t nrb_kmeans_update_workspace(int64_t n, int32_t k) {
+    return counting_sort_ws(n, k) + align_up((size_t)(k + 2) * sizeof(int), 256) +
+           align_up((size_t)(n > 0 ? n : 1) * sizeof(int), 256);
+}
+
+extern "C" int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32_t kp,
+                                 const int64_t* assign, int32_t k, float* centroids,
+                                 float* hassign, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    NRB_REQUIRE(n >= 0 && n < (1LL << 31) && k > 0 && d > 0 && kp >= d && kp % 32 == 0 && kp <= 2048,
+                "kmeans_update: bad sizes n=%lld k=%d d=%d kp=%d", (long long)n, k, d, kp);
+    if (workspace_bytes < nrb_kmeans_update_workspace(n, k)) {
+        set_error("kmeans_update: workspace too small");
+        return NRB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    const size_t cs = counting_sort_ws(n, k);
+    int* offsets = (int*)(w + cs);
+    int* order = (int*)(w + cs + align_up((size_t)(k + 2) * sizeof(int), 256));
+    int rc = launch_counting_sort_i64(assign, n, k, offsets, order, nullptr, w, cs, st);
+    if (rc) return rc;
+    constexpr int RS = 4;
+    const int threads = (kp / 4) * RS;
+    NRB_REQUIRE(threads <= 1024, "kmeans_update: kp %d too large", kp);
+    const size_t smem = (size_t)RS * kp * sizeof(double);
+    if (smem > 48 * 1024)
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(kmeans_update_kernel<RS>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kmeans_update_kernel<RS><<<k, threads, smem, st>>>(x_raw, kp, d, offsets, order, centroids, hassign);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+extern "C" int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts, int64_t nq,
+                              int32_t k, int32_t metric, float* D, int64_t* I, void* stream) {
+    NRB_REQUIRE(nparts > 0 && nq >= 0 && k > 0, "merge_topk: bad sizes");
+    if (nq == 0) return NRB_OK;
+    const int P = pow2_ge(nparts * k);
+    NRB_REQUIRE(P <= 16384, "merge_topk: nparts*k = %d too large", nparts * k);
+    const size_t smem = (size_t)P * sizeof(uint64_t);
+    if (smem > 48 * 1024)
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = P / 2;
+    threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
+    merge_kernel<<<(unsigned)nq, threads, smem, (cudaStream_t)stream>>>(Dp, Ip, nparts, nq, k, P, metric, D, I);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}

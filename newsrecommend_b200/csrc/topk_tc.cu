@@ -1,0 +1,355 @@
+// K2: fused distance + selection on the 5th-generation tensor cores (NRB_PATH_TC).
+//
+// Stands in for faiss's exhaustive_inner_product_blas / exhaustive_L2sqr_blas (sgemm blocks +
+// HeapBlockResultHandler) behind IndexFlat::search, i.e. Retrieval.py:21,32 and the assignment
+// search inside Clustering::train (Retrieval.py:18).
+//
+// One persistent CTA per SM walks a list of Units (128 query rows x a run of item rows). Per
+// 128 x 256 score tile:
+//   warp 0  (1 lane)  TMA producer: hi/lo planes of the query tile and the item tile, K chunks
+//                     of 32 fp32 (128-byte swizzled rows), 2-stage mbarrier ring
+//   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
+//                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
+//   warps 2-5         epilogue: tcgen05.ld the 128 x 256 accumulator (one query row per thread),
+//                     turn scores into keys, append everything above the row's running
+//                     threshold to the row's candidate buffer; a warp-cooperative bitonic
+//                     prune brings a full buffer back to the best k and raises the threshold.
+// TMEM holds two accumulators (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of
+// tile t+1. The score matrix never exists in HBM.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace nrb {
+
+namespace {
+
+constexpr int BM = 128;   // query rows per tile (= TMEM lanes)
+constexpr int BN = 256;   // item rows per tile (= TMEM columns per accumulator)
+constexpr int KC = 32;    // fp32 elements per K chunk (128-byte swizzle span)
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * KC * 4;
+constexpr int B_BYTES = BN * KC * 4;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct TcShared {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    float nrm[2][BN];
+};
+
+constexpr size_t TC_SMEM = (size_t)STAGES * STAGE_BYTES + sizeof(TcShared) + 1024;
+
+template <bool L2>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+               const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+               const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc, int k,
+               const float* __restrict__ a_norms, const float* __restrict__ b_norms,
+               int64_t a_total, int64_t b_total, float* __restrict__ part_key,
+               int* __restrict__ part_idx, float* __restrict__ cand_key_buf,
+               int* __restrict__ cand_idx_buf) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)STAGES * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_units = *n_units_p;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&sh->full[s], 1);
+            ptx::mbar_init(&sh->empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&sh->tfull[a], 1);
+            ptx::mbar_init(&sh->tempty[a], 4);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&map_ah);
+        ptx::prefetch_tensormap(&map_al);
+        ptx::prefetch_tensormap(&map_bh);
+        ptx::prefetch_tensormap(&map_bl);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&sh->tmem_base, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const Unit un = units[u];
+                const int ntiles = (un.b_rows + BN - 1) / BN;
+                for (int t = 0; t < ntiles; t++) {
+                    const int brow = un.b_row0 + t * BN;
+                    for (int kc = 0; kc < nkc; kc++) {
+                        ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+                        ptx::mbar_arrive_expect_tx(&sh->full[stage], STAGE_BYTES);
+                        ptx::tma_load_2d(st, &map_ah, &sh->full[stage], kc * KC, un.a_row0);
+                        ptx::tma_load_2d(st + A_BYTES, &map_al, &sh->full[stage], kc * KC, un.a_row0);
+                        ptx::tma_load_2d(st + 2 * A_BYTES, &map_bh, &sh->full[stage], kc * KC, brow);
+                        ptx::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_bl, &sh->full[stage], kc * KC, brow);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const Unit un = units[u];
+                const int ntiles = (un.b_rows + BN - 1) / BN;
+                for (int t = 0; t < ntiles; t++) {
+                    ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kc = 0; kc < nkc; kc++) {
+                        ptx::mbar_wait(&sh->full[stage], phase);
+                        ptx::tcgen05_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                        const uint32_t s_ah = sa, s_al = sa + A_BYTES, s_bh = sa + 2 * A_BYTES,
+                                       s_bl = sa + 2 * A_BYTES + B_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ks++) {
+                            const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes inside the swizzled row
+                            const uint64_t d_ah = ptx::umma_desc_sw128(s_ah + off);
+                            const uint64_t d_al = ptx::umma_desc_sw128(s_al + off);
+                            const uint64_t d_bh = ptx::umma_desc_sw128(s_bh + off);
+                            const uint64_t d_bl = ptx::umma_desc_sw128(s_bl + off);
+                            ptx::umma_tf32(d_tmem, d_al, d_bh, idesc, (kc | ks) != 0);
+                            ptx::umma_tf32(d_tmem, d_ah, d_bl, idesc, 1);
+                            ptx::umma_tf32(d_tmem, d_ah, d_bh, idesc, 1);
+                        }
+                        ptx::umma_commit(&sh->empty[stage]);  // frees the smem stage when the MMAs retire
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    ptx::umma_commit(&sh->tfull[acc]);  // accumulator complete
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ selection epilogue
+        const int quad = warp & 3;            // TMEM lane quarter this warp may read
+        const int row = quad * 32 + lane;     // query row inside the tile
+        const int etid = (warp - 2) * 32 + lane;
+        float* ck = cand_key_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;  // warp's 32 rows
+        int* ci = cand_idx_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
+        float* myk = ck + (int64_t)lane * CAND_CAP;
+        int* myi = ci + (int64_t)lane * CAND_CAP;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const Unit un = units[u];
+            const int ntiles = (un.b_rows + BN - 1) / BN;
+            int cnt = 0;
+            float thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
+            float qn = 0.f;
+            if (L2) {
+                const int64_t ar = (int64_t)un.a_row0 + row;
+                qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
+            }
+            for (int t = 0; t < ntiles; t++) {
+                const int col_base = t * BN;  // column offset inside the unit
+                const int valid = un.b_rows - col_base;
+                if (L2) {
+                    // stage the tile's item norms; the named barrier also orders reuse of nrm[acc]
+                    for (int c = etid; c < BN; c += 128) {
+                        const int64_t br = (int64_t)un.b_row0 + col_base + c;
+                        sh->nrm[acc][c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                ptx::mbar_wait(&sh->tfull[acc], acc_phase);
+                ptx::tcgen05_fence_after();
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (c0 >= valid) break;  // warp-uniform
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
+                    ptx::tmem_ld_wait();
+                    float f[32];
+                    float m = NEG_INF;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        float x = __uint_as_float(v[i]);
+                        if (L2) x = -fmaxf(qn + sh->nrm[acc][c0 + i] - 2.f * x, 0.f);
+                        if (c0 + i >= valid) x = NEG_INF;
+                        f[i] = x;
+                        m = fmaxf(m, x);
+                    }
+                    if (m > thr) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            if (f[i] > thr) {
+                                myk[cnt] = f[i];
+                                myi[cnt] = un.b_row0 + col_base + c0 + i;
+                                cnt++;
+                            }
+                        }
+                    }
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > CAND_CAP - 32);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n = __shfl_sync(0xffffffffu, cnt, src);
+                        float* rk = ck + (int64_t)src * CAND_CAP;
+                        int* ri = ci + (int64_t)src * CAND_CAP;
+                        const float tnew = warp_prune_row(rk, ri, n, k, rk, ri, lane);
+                        if (lane == src) {
+                            cnt = n < k ? n : k;
+                            thr = tnew;
+                        }
+                    }
+                }
+                // accumulator drained: hand it back to the MMA warp
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&sh->tempty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            // unit done: best-first top-k of every row into the unit's partial rows
+            for (int src = 0; src < 32; src++) {
+                const int n = __shfl_sync(0xffffffffu, cnt, src);
+                const int64_t o = ((int64_t)u * UNIT_ROWS + quad * 32 + src) * k;
+                warp_prune_row(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k,
+                               part_key + o, part_idx + o, lane);
+            }
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// Tensor map over a [rows, kp] fp32 plane, box = KC columns x box_rows rows, 128-byte swizzle.
+int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int kp, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return NRB_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)(rows > 0 ? rows : 1)};
+    cuuint64_t gstr[1] = {(cuuint64_t)kp * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld kp=%d)", (int)r, (long long)rows, kp);
+        return NRB_ERR_CUDA;
+    }
+    return NRB_OK;
+}
+
+}  // namespace
+
+int tc_available() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    return p.major == 10 ? 1 : 0;
+}
+
+int tc_grid(int n_units) {
+    int g = sm_count();
+    if (n_units > 0 && n_units < g) g = n_units;
+    return g < 1 ? 1 : g;
+}
+
+size_t tc_scratch_bytes(int grid) {
+    return (size_t)grid * BM * CAND_CAP * (sizeof(float) + sizeof(int)) + 256;
+}
+
+int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
+                       const int* n_units_dev, int grid, int metric, int k, float* part_key,
+                       int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    NRB_REQUIRE(a->hi && a->lo && b->hi && b->lo, "tc: hi/lo planes required");
+    NRB_REQUIRE(a->kp == b->kp && a->kp % KC == 0 && a->kp >= KC, "tc: kp mismatch / not a multiple of %d", KC);
+    NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "tc: k=%d out of range [1,%d]", k, NRB_MAX_K);
+    NRB_REQUIRE(metric != NRB_METRIC_L2 || (a->norms && b->norms), "tc: norms required for L2");
+    if (scratch_bytes < tc_scratch_bytes(grid)) {
+        set_error("tc: scratch too small");
+        return NRB_ERR_WORKSPACE;
+    }
+    CUtensorMap mah, mal, mbh, mbl;
+    int rc;
+    if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
+    if ((rc = make_plane_map(&mal, a->lo, a->n, a->kp, BM))) return rc;
+    if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN))) return rc;
+    if ((rc = make_plane_map(&mbl, b->lo, b->n, b->kp, BN))) return rc;
+    float* ck = (float*)scratch;
+    int* ci = (int*)((char*)scratch + (size_t)grid * BM * CAND_CAP * sizeof(float));
+    const int nkc = a->kp / KC;
+    if (metric == NRB_METRIC_L2) {
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        topk_tc_kernel<true><<<grid, NUM_THREADS, TC_SMEM, st>>>(mah, mal, mbh, mbl, units, n_units_dev, nkc, k,
+                                                                 a->norms, b->norms, a->n, b->n, part_key,
+                                                                 part_idx, ck, ci);
+    } else {
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        topk_tc_kernel<false><<<grid, NUM_THREADS, TC_SMEM, st>>>(mah, mal, mbh, mbl, units, n_units_dev, nkc, k,
+                                                                  a->norms, b->norms, a->n, b->n, part_key,
+                                                                  part_idx, ck, ci);
+    }
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+}  // namespace nrb

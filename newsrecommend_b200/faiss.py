@@ -1,0 +1,507 @@
+"""`faiss`-compatible surface of the B200 candidate-retrieval path.
+
+Mirrors exactly the symbols /root/reference/Retrieval.py uses (Retrieval.py:12-32: Clustering,
+IndexHNSWFlat, IndexFlatL2, vector_float_to_array, index.search) plus the index surface
+BASELINE.json's north_star names (IndexFlatIP, IndexIVFFlat with train/add/search, nlist /
+nprobe / k semantics, METRIC_*, normalize_L2). Semantics follow SURVEY.md section 8b.
+
+Host code only: every array lives in HBM as torch tensors and all arithmetic is done by
+libnrb200.so (hand-written sm_100a CUDA) through the C-ABI in include/nrb200.h. numpy in ->
+numpy out (synchronous, like faiss); CUDA torch tensors in -> CUDA torch tensors out
+(asynchronous on the current stream). No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import METRIC_INNER_PRODUCT, METRIC_L2, PATH_AUTO, PATH_SIMT, PATH_TC, Matrix, check, lib
+
+__all__ = [
+    "METRIC_INNER_PRODUCT", "METRIC_L2", "IndexFlat", "IndexFlatL2", "IndexFlatIP", "IndexHNSWFlat",
+    "IndexIVFFlat", "Clustering", "ClusteringParameters", "vector_float_to_array", "normalize_L2",
+]
+
+IVF_QUERY_BATCH = 65536  # queries per nrb_ivf_search call (bounds the regrouped query planes)
+
+
+# ------------------------------------------------------------------------------------ helpers
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("newsrecommend_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _round_kp(d: int) -> int:
+    return (d + 31) // 32 * 32
+
+
+def _to_device_f32(x):
+    """Returns (2-D fp32 CUDA tensor with unit column stride, came_from_numpy)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+        if t.dtype != torch.float32:
+            t = t.float()
+        if not t.is_cuda:
+            t = t.to(_device(), non_blocking=True)
+        from_np = False
+    else:
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        t = torch.from_numpy(a).to(_device(), non_blocking=True)
+        from_np = True
+    assert t.dim() == 2, "expected a 2-D array"
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t, from_np
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy()
+
+
+class PackedMatrix:
+    """Device form of a row-major fp32 matrix: zero-padded raw rows, tf32 hi / lo planes and
+    squared norms (struct nrb_matrix). Grows geometrically on append."""
+
+    def __init__(self, d: int, device=None, planes=("raw", "hi", "lo", "norms")):
+        self.d = d
+        self.kp = _round_kp(d)
+        self.n = 0
+        self.device = device or _device()
+        self.planes = planes
+        self._cap = 0
+        self.raw = self.hi = self.lo = self.norms = None
+
+    def _reserve(self, n: int):
+        if n <= self._cap:
+            return
+        cap = max(n, int(self._cap * 1.5), 128)
+        for name in self.planes:
+            shape = (cap,) if name == "norms" else (cap, self.kp)
+            new = torch.empty(shape, dtype=torch.float32, device=self.device)
+            old = getattr(self, name)
+            if old is not None and self.n:
+                new[: self.n].copy_(old[: self.n])
+            setattr(self, name, new)
+        self._cap = cap
+
+    def append(self, x: torch.Tensor):
+        """x: fp32 CUDA [m, d] (row stride arbitrary)."""
+        m = x.shape[0]
+        assert x.shape[1] == self.d
+        self._reserve(self.n + m)
+        if m:
+            off = self.n
+            check(lib.nrb_pack_rows(
+                x.data_ptr(), m, self.d, x.stride(0), self.kp,
+                _ptr(self.raw[off:]) if self.raw is not None else 0,
+                _ptr(self.hi[off:]) if self.hi is not None else 0,
+                _ptr(self.lo[off:]) if self.lo is not None else 0,
+                _ptr(self.norms[off:]) if self.norms is not None else 0, _stream()), "pack_rows")
+        self.n += m
+
+    def clear(self):
+        self.n = 0
+
+    def struct(self, row0: int = 0, rows: int | None = None) -> Matrix:
+        rows = self.n - row0 if rows is None else rows
+        m = Matrix()
+        m.raw = _ptr(self.raw[row0:]) if self.raw is not None else None
+        m.hi = _ptr(self.hi[row0:]) if self.hi is not None else None
+        m.lo = _ptr(self.lo[row0:]) if self.lo is not None else None
+        m.norms = _ptr(self.norms[row0:]) if self.norms is not None else None
+        m.n, m.d, m.kp = rows, self.d, self.kp
+        return m
+
+    @classmethod
+    def from_tensor(cls, x: torch.Tensor, planes=("raw", "hi", "lo", "norms")):
+        p = cls(x.shape[1], x.device, planes)
+        p.append(x)
+        return p
+
+
+def _search_flat_dev(q: PackedMatrix, b: PackedMatrix, metric: int, k: int, id_base: int = 0,
+                     path: int = PATH_AUTO):
+    """nrb_search_flat on packed matrices -> (D f32[nq,k], I i64[nq,k]) CUDA tensors."""
+    nq = q.n
+    D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    if nq == 0:
+        return D, I
+    wsb = lib.nrb_search_flat_workspace(nq, b.n, k, q.kp)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=q.device)
+    qs, bs = q.struct(), b.struct()
+    check(lib.nrb_search_flat(C.byref(qs), C.byref(bs), metric, k, id_base, D.data_ptr(), I.data_ptr(),
+                              ws.data_ptr(), wsb, path, _stream()), "search_flat")
+    return D, I
+
+
+# ------------------------------------------------------------------------------------ flat
+class IndexFlat:
+    """IndexFlatL2 / IndexFlatIP (Retrieval.py:25-26,32). add() copies into HBM."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2):
+        self.d = int(d)
+        self.metric_type = metric
+        self.is_trained = True
+        self.verbose = False
+        self.path = PATH_AUTO  # PATH_SIMT forces the fp32 CUDA-core kernels
+        self._xb: PackedMatrix | None = None
+
+    @property
+    def ntotal(self) -> int:
+        return 0 if self._xb is None else self._xb.n
+
+    def train(self, x):
+        pass
+
+    def add(self, x):
+        t, _ = _to_device_f32(x)
+        assert t.shape[1] == self.d
+        if self._xb is None:
+            self._xb = PackedMatrix(self.d, t.device)
+        self._xb.append(t)
+
+    def reset(self):
+        if self._xb is not None:
+            self._xb.clear()
+
+    def _packed(self) -> PackedMatrix:
+        if self._xb is None:
+            self._xb = PackedMatrix(self.d)
+        return self._xb
+
+    def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0):
+        return _search_flat_dev(q, self._packed(), self.metric_type, k, id_base, self.path)
+
+    def search(self, x, k: int):
+        t, from_np = _to_device_f32(x)
+        assert t.shape[1] == self.d
+        assert k > 0
+        if k > _lib.MAX_K:
+            raise RuntimeError(f"k={k} > {_lib.MAX_K} is not supported by the selection stage")
+        q = PackedMatrix.from_tensor(t, planes=self._query_planes())
+        D, I = self.search_packed(q, int(k))
+        if from_np:
+            return _to_host(D), _to_host(I)
+        return D, I
+
+    def _query_planes(self):
+        need = ("raw",) if self.path == PATH_SIMT else ("hi", "lo")
+        return need + (("norms",) if self.metric_type == METRIC_L2 else ())
+
+    def assign(self, x, k: int = 1):
+        return self.search(x, k)[1]
+
+    def reconstruct_n(self, i0: int = 0, n: int | None = None) -> np.ndarray:
+        n = self.ntotal - i0 if n is None else n
+        return _to_host(self._packed().raw[i0:i0 + n, : self.d].contiguous())
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d: int):
+        super().__init__(d, METRIC_L2)
+
+
+class IndexFlatIP(IndexFlat):
+    def __init__(self, d: int):
+        super().__init__(d, METRIC_INNER_PRODUCT)
+
+
+class IndexHNSWFlat(IndexFlatL2):
+    """Accepted for Retrieval.py:16. The reference uses HNSW(M=32) only as the k-means assigner
+    over <= 325 centroids; its parallel graph build is nondeterministic, so it cannot be
+    reproduced bit for bit even by faiss itself. Here it is an EXACT L2 index (what
+    IndexIVFFlat.train uses); documented divergence, SURVEY 8a row a3."""
+
+    def __init__(self, d: int, M: int = 32):
+        super().__init__(d)
+        self.M = M
+
+
+# ------------------------------------------------------------------------------------ k-means
+class ClusteringParameters:
+    def __init__(self):
+        self.niter = 25
+        self.nredo = 1
+        self.verbose = False
+        self.spherical = False
+        self.int_centroids = False
+        self.update_index = False
+        self.frozen_centroids = False
+        self.min_points_per_centroid = 39
+        self.max_points_per_centroid = 256
+        self.seed = 1234
+        self.decode_block_size = 32768
+
+
+class ClusteringIterationStats:
+    def __init__(self, obj, imbalance_factor, nsplit):
+        self.obj = obj
+        self.imbalance_factor = imbalance_factor
+        self.nsplit = nsplit
+
+
+def rand_perm(n: int, seed: int) -> np.ndarray:
+    """faiss::rand_perm through the C-ABI host helper (std::mt19937)."""
+    perm = np.empty(n, dtype=np.int32)
+    check(lib.nrb_rand_perm_host(perm.ctypes.data, n, seed), "rand_perm")
+    return perm
+
+
+def kmeans_update(x: PackedMatrix, assign: torch.Tensor, k: int):
+    """One centroid update (K1b): returns (centroids f32[k,d], hassign f32[k]) CUDA tensors."""
+    cent = torch.empty((k, x.d), dtype=torch.float32, device=x.device)
+    hassign = torch.empty((k,), dtype=torch.float32, device=x.device)
+    wsb = lib.nrb_kmeans_update_workspace(x.n, k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    check(lib.nrb_kmeans_update(x.raw.data_ptr(), x.n, x.d, x.kp, assign.data_ptr(), k, cent.data_ptr(),
+                                hassign.data_ptr(), ws.data_ptr(), wsb, _stream()), "kmeans_update")
+    return cent, hassign
+
+
+class Clustering(ClusteringParameters):
+    """faiss.Clustering(d, k) as used at Retrieval.py:12-19: Lloyd k-means with faiss's
+    subsampling (256*k rows, rand_perm seed), random-row init (seed+1), mean update and
+    empty-cluster split. Assignment = exact search on `index` (K2 with k=1), update = K1b."""
+
+    def __init__(self, d: int, k: int, cp: ClusteringParameters | None = None):
+        super().__init__()
+        if cp is not None:
+            self.__dict__.update(cp.__dict__)
+        self.d = int(d)
+        self.k = int(k)
+        self.centroids = np.empty(0, dtype=np.float32)
+        self.iteration_stats = []
+        self.trace = None  # hook(it, centroids_in, assign, centroids_out) with numpy arrays
+
+    def train(self, x, index):
+        t, _ = _to_device_f32(x)
+        n, d = t.shape
+        k = self.k
+        assert d == self.d
+        if n < k:
+            raise RuntimeError("Number of training points (%d) should be at least as large as number of "
+                               "clusters (%d)" % (n, k))
+        if not bool(torch.isfinite(t).all()):
+            raise RuntimeError("input contains NaN's or Inf's")
+        dev = t.device
+        if n > k * self.max_points_per_centroid:
+            perm = rand_perm(n, self.seed)[: k * self.max_points_per_centroid]
+            sel = torch.from_numpy(perm.astype(np.int64)).to(dev)
+            t = t.index_select(0, sel)
+            n = t.shape[0]
+        elif n < k * self.min_points_per_centroid:
+            print("WARNING clustering %d points to %d centroids: please provide at least %d training points"
+                  % (n, k, k * self.min_points_per_centroid), file=sys.stderr)
+        if n == k:
+            self.centroids = _to_host(t.contiguous()).reshape(-1)
+            index.reset()
+            index.add(t)
+            return
+        xs = PackedMatrix.from_tensor(t)
+        best = None
+        for redo in range(self.nredo):
+            perm = rand_perm(n, self.seed + 1 + redo * 15486557)[:k]
+            cent = t.index_select(0, torch.from_numpy(perm.astype(np.int64)).to(dev)).contiguous()
+            if self.spherical:
+                check(lib.nrb_normalize_l2(cent.data_ptr(), k, d, d, _stream()), "normalize_l2")
+            if index.ntotal != 0:
+                index.reset()
+            index.add(cent)
+            stats = []
+            obj = 0.0
+            for it in range(self.niter):
+                Dd, assign = index.search_packed(xs, 1)
+                assign = assign.reshape(-1)
+                obj_t = Dd.sum()
+                cent_in = cent
+                cent, hassign = kmeans_update(xs, assign, k)
+                hass = _to_host(hassign)
+                imb = float((hass.astype(np.float64) ** 2).sum() * k / float(n) ** 2)
+                nsplit = 0
+                if (hass == 0).any():
+                    ch = _to_host(cent)
+                    nsplit = check(lib.nrb_split_clusters_host(d, k, n, hass.ctypes.data, ch.ctypes.data),
+                                   "split_clusters")
+                    cent = torch.from_numpy(ch).to(dev)
+                if self.spherical:
+                    check(lib.nrb_normalize_l2(cent.data_ptr(), k, d, d, _stream()), "normalize_l2")
+                obj = float(obj_t)
+                stats.append(ClusteringIterationStats(obj, imb, nsplit))
+                if self.verbose:
+                    print("  Iteration %d objective=%g imbalance=%.3f nsplit=%d" % (it, obj, imb, nsplit))
+                if self.trace is not None:
+                    self.trace(it, _to_host(cent_in), _to_host(assign), _to_host(cent))
+                index.reset()
+                index.add(cent)
+            if self.nredo > 1:
+                better = best is None or (obj > best[0] if index.metric_type == METRIC_INNER_PRODUCT
+                                          else obj < best[0])
+                if better:
+                    best = (obj, cent.clone(), stats)
+            else:
+                best = (obj, cent, stats)
+        _, cent, stats = best
+        if self.nredo > 1:
+            index.reset()
+            index.add(cent)
+        self.centroids = _to_host(cent).reshape(-1)
+        self.iteration_stats = stats
+
+
+def vector_float_to_array(v) -> np.ndarray:
+    """Retrieval.py:19 -- copy of the centroid vector as a numpy array."""
+    return np.array(v, dtype=np.float32, copy=True)
+
+
+def normalize_L2(x):
+    """faiss.normalize_L2: in place on a numpy array or CUDA tensor; zero rows untouched."""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
+        check(lib.nrb_normalize_l2(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), _stream()), "normalize_l2")
+        return
+    assert isinstance(x, np.ndarray) and x.dtype == np.float32 and x.ndim == 2
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(_device())
+    check(lib.nrb_normalize_l2(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), _stream()), "normalize_l2")
+    x[...] = _to_host(t)
+
+
+# ------------------------------------------------------------------------------------ IVF
+class IndexIVFFlat:
+    """IndexIVFFlat(quantizer, d, nlist, metric): train = k-means on the quantizer (cp.niter =
+    10), add = nearest centroid + list-contiguous layout, search = coarse top-nprobe + list
+    scan. In the reference this is the hand-rolled k-means -> cluster_to_articles
+    -> nearest-centroid pipeline of Retrieval.py:11-34."""
+
+    def __init__(self, quantizer: IndexFlat, d: int, nlist: int, metric: int = METRIC_L2):
+        self.quantizer = quantizer
+        self.d = int(d)
+        self.nlist = int(nlist)
+        self.metric_type = metric
+        self.nprobe = 1
+        self.is_trained = False
+        self.verbose = False
+        self.path = PATH_AUTO
+        self.cp = ClusteringParameters()
+        self.cp.niter = 10
+        self.clustering = None
+        self._x: PackedMatrix | None = None   # rows in insertion order (raw plane only)
+        self._assign = None                   # i64[ntotal] list of every row
+        self._lists = None                    # dict built lazily: packed planes in list order
+
+    @property
+    def ntotal(self) -> int:
+        return 0 if self._x is None else self._x.n
+
+    def train(self, x):
+        if self.quantizer.is_trained and self.quantizer.ntotal == self.nlist:
+            self.is_trained = True
+            return
+        clus = Clustering(self.d, self.nlist, self.cp)
+        clus.verbose = self.verbose or self.cp.verbose
+        self.quantizer.reset()
+        clus.train(x, self.quantizer)
+        self.clustering = clus
+        self.is_trained = True
+
+    def add(self, x):
+        if not self.is_trained:
+            raise RuntimeError("Error: 'is_trained' failed")
+        t, _ = _to_device_f32(x)
+        assert t.shape[1] == self.d
+        if self._x is None:
+            self._x = PackedMatrix(self.d, t.device, planes=("raw",))
+        q = PackedMatrix.from_tensor(t, planes=self.quantizer._query_planes())
+        _, a = self.quantizer.search_packed(q, 1)
+        a = a.reshape(-1)
+        self._assign = a if self._assign is None or self._x.n == 0 else torch.cat([self._assign, a])
+        self._x.append(t)
+        self._lists = None
+
+    def reset(self):
+        if self._x is not None:
+            self._x.clear()
+        self._assign = None
+        self._lists = None
+
+    def _build_lists(self):
+        if self._lists is not None:
+            return self._lists
+        n, dev = self.ntotal, self._x.device
+        offsets = torch.empty(self.nlist + 1, dtype=torch.int32, device=dev)
+        order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        wsb = lib.nrb_ivf_build_lists_workspace(n, self.nlist)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.nrb_ivf_build_lists(self._assign.data_ptr(), n, self.nlist, offsets.data_ptr(),
+                                      order.data_ptr(), ws.data_ptr(), wsb, _stream()), "ivf_build_lists")
+        kp = self._x.kp
+        raw = torch.empty((max(n, 1), kp), dtype=torch.float32, device=dev)
+        check(lib.nrb_gather_rows(self._x.raw.data_ptr(), kp, order.data_ptr(), n, raw.data_ptr(), _stream()),
+              "gather_rows")
+        packed = PackedMatrix(self.d, dev)
+        packed._reserve(n)
+        packed.raw = raw  # already list-ordered and padded; derive hi / lo / norms from it
+        check(lib.nrb_pack_rows(raw.data_ptr(), n, self.d, kp, kp, 0, packed.hi.data_ptr(), packed.lo.data_ptr(),
+                                packed.norms.data_ptr(), _stream()), "pack_rows")
+        packed.n = n
+        ids = order[:n].to(torch.int64)  # ids are sequential: id = insertion row
+        off_h = _to_host(offsets).astype(np.int64)
+        sizes = np.diff(off_h)
+        self._lists = dict(packed=packed, ids=ids, offsets=offsets, offsets_host=off_h,
+                           max_len=int(sizes.max()) if sizes.size else 0)
+        return self._lists
+
+    def list_sizes(self) -> np.ndarray:
+        return np.diff(self._build_lists()["offsets_host"])
+
+    def search(self, x, k: int):
+        if not self.is_trained:
+            raise RuntimeError("Error: 'is_trained' failed")
+        t, from_np = _to_device_f32(x)
+        assert t.shape[1] == self.d
+        assert k > 0
+        nprobe = min(int(self.nprobe), self.nlist)
+        if k > _lib.MAX_K or nprobe > _lib.MAX_K:
+            raise RuntimeError(f"k / nprobe > {_lib.MAX_K} is not supported by the selection stage")
+        nq, dev = t.shape[0], t.device
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if self.ntotal == 0:
+            D.fill_(3.4028234663852886e38 if self.metric_type == METRIC_L2 else -3.4028234663852886e38)
+            I.fill_(-1)
+        elif nq:
+            L = self._build_lists()
+            planes = ("raw",) if self.path == PATH_SIMT else ("hi", "lo")
+            planes = tuple(dict.fromkeys(planes + self.quantizer._query_planes() +
+                                         (("norms",) if self.metric_type == METRIC_L2 else ())))
+            ls = L["packed"].struct()
+            for q0 in range(0, nq, IVF_QUERY_BATCH):
+                q1 = min(nq, q0 + IVF_QUERY_BATCH)
+                q = PackedMatrix.from_tensor(t[q0:q1], planes=planes)
+                _, coarse = self.quantizer.search_packed(q, nprobe)
+                wsb = lib.nrb_ivf_search_workspace(q.n, nprobe, k, q.kp, self.nlist, L["max_len"])
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                qs = q.struct()
+                check(lib.nrb_ivf_search(C.byref(qs), C.byref(ls), L["offsets"].data_ptr(), self.nlist,
+                                         L["max_len"], L["ids"].data_ptr(), coarse.data_ptr(), nprobe,
+                                         self.metric_type, int(k), D[q0:q1].data_ptr(), I[q0:q1].data_ptr(),
+                                         ws.data_ptr(), wsb, self.path, _stream()), "ivf_search")
+        if from_np:
+            return _to_host(D), _to_host(I)
+        return D, I

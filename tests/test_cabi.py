@@ -1,0 +1,112 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol that
+include/nrb200.h declares, its host helpers agree with the oracle, and the compute entry points
+fail loudly (no CPU fallback) when there is no device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from newsrecommend_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nrb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nrb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(_lib.lib, s), f"libnrb200.so does not export {s}"
+    assert sorted(_lib.SYMBOLS) == syms
+
+
+def test_library_has_no_torch_or_libcuda_link_dependency():
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libcuda.so" not in out and "libc10" not in out
+
+
+def test_version_and_error_buffer():
+    assert _lib.lib.nrb_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_rand_perm_host_matches_oracle(oracle):
+    for n, seed in ((1, 1), (17, 1234), (5000, 1235)):
+        perm = np.empty(n, dtype=np.int32)
+        assert _lib.lib.nrb_rand_perm_host(perm.ctypes.data, n, seed) == 0
+        assert np.array_equal(perm, oracle.rand_perm(n, seed))
+
+
+def test_split_clusters_host_matches_oracle(oracle):
+    rng = np.random.default_rng(0)
+    k, d, n = 12, 10, 500
+    cent = rng.standard_normal((k, d)).astype(np.float32)
+    h = rng.integers(5, 80, size=k).astype(np.float32)
+    h[[2, 7, 11]] = 0
+    c1, h1 = cent.copy(), h.copy()
+    c2, h2 = cent.copy(), h.copy()
+    ns1 = oracle.split_clusters(c1, h1, n)
+    ns2 = _lib.lib.nrb_split_clusters_host(d, k, n, h2.ctypes.data, c2.ctypes.data)
+    assert ns1 == ns2 == 3
+    assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    q = _lib.Matrix()
+    b = _lib.Matrix()
+    q.n, q.d, q.kp = 4, 32, 32
+    b.n, b.d, b.kp = 4, 32, 32
+    D = np.zeros((4, 1), dtype=np.float32)
+    I = np.zeros((4, 1), dtype=np.int64)
+    rc = _lib.lib.nrb_search_flat(C.byref(q), C.byref(b), 0, 1, 0, D.ctypes.data, I.ctypes.data, None, 0, 0, None)
+    assert rc == -3  # NRB_ERR_NO_DEVICE
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA device"):
+        _lib.check(rc, "search_flat")
+    import newsrecommend_b200.faiss as nf
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nf.IndexFlatIP(8).add(np.zeros((2, 8), dtype=np.float32))
+
+
+def test_argument_validation():
+    q = _lib.Matrix()
+    b = _lib.Matrix()
+    q.n, q.d, q.kp = 4, 32, 32
+    b.n, b.d, b.kp = 4, 16, 32
+    D = np.zeros((4, 1), dtype=np.float32)
+    I = np.zeros((4, 1), dtype=np.int64)
+    rc = _lib.lib.nrb_search_flat(C.byref(q), C.byref(b), 0, 1, 0, D.ctypes.data, I.ctypes.data, None, 0, 0, None)
+    assert rc == -1 and "dimension mismatch" in _lib.last_error()
+    b.d = 32
+    rc = _lib.lib.nrb_search_flat(C.byref(q), C.byref(b), 0, 1000, 0, D.ctypes.data, I.ctypes.data, None, 0, 0, None)
+    assert rc == -1 and "out of range" in _lib.last_error()
+
+
+def test_shim_exposes_reference_surface():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "shim"))
+    try:
+        import faiss  # the shim
+        for name in ("Clustering", "IndexHNSWFlat", "IndexFlatL2", "IndexFlatIP", "IndexIVFFlat",
+                     "vector_float_to_array", "normalize_L2", "METRIC_L2", "METRIC_INNER_PRODUCT"):
+            assert hasattr(faiss, name), name
+        c = faiss.Clustering(256, 300)  # Retrieval.py:12-14
+        c.niter = 80
+        c.verbose = True
+        assert (c.seed, c.max_points_per_centroid, c.min_points_per_centroid, c.nredo) == (1234, 256, 39, 1)
+        ivf_cp = faiss.IndexIVFFlat(faiss.IndexFlatL2(8), 8, 4).cp
+        assert ivf_cp.niter == 10
+        v = faiss.vector_float_to_array([1.0, 2.0])
+        assert v.dtype == np.float32
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("faiss", None)

@@ -1,0 +1,170 @@
+"""GPU parity tests of the exact top-k path (K0 pack, K2 distance+selection, select) against the
+oracle, through the faiss-compatible surface and the C-ABI. Bit-exact ids outside sub-1e-5 gaps,
+scores within 1e-4 relative (tolerances of BASELINE.json's north_star, see parity.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from newsrecommend_b200.parity import compare_topk
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PATHS = {"tc": 2, "simt": 1}
+
+
+def _search(nf, xb, xq, k, metric, path):
+    index = nf.IndexFlatIP(xb.shape[1]) if metric == 0 else nf.IndexFlatL2(xb.shape[1])
+    index.path = PATHS[path]
+    index.add(xb)
+    assert index.ntotal == xb.shape[0]
+    return index.search(xq, k)
+
+
+def test_pack_rows_split_is_exact(nf):
+    import torch
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1000, 250), dtype=np.float32) * np.float32(3.0)
+    p = nf.PackedMatrix.from_tensor(torch.from_numpy(x).cuda())
+    raw, hi, lo = p.raw[:1000].cpu().numpy(), p.hi[:1000].cpu().numpy(), p.lo[:1000].cpu().numpy()
+    assert p.kp == 256 and np.array_equal(raw[:, :250], x) and (raw[:, 250:] == 0).all()
+    assert (hi.view(np.uint32) & 0x1FFF == 0).all() and (lo.view(np.uint32) & 0x1FFF == 0).all()
+    # hi + lo reproduces x to ~2^-22 relative (two tf32 mantissas)
+    err = np.abs((hi.astype(np.float64) + lo.astype(np.float64))[:, :250] - x)
+    assert (err <= np.abs(x) * 2.0 ** -21 + 1e-30).all()
+    assert np.allclose(p.norms[:1000].cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_golden_fixture(nf, path, metric):
+    g = np.load(os.path.join(GOLDEN, "flat_small.npz"))
+    D, I = _search(nf, g["xb"], g["xq"], 10, metric, path)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (48, 10)
+    rep = compare_topk(D, I, g[f"D{metric}"], g[f"I{metric}"], metric)
+    assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("nq,nb,d,k", [
+    (1, 5000, 250, 50), (19, 5000, 250, 50), (20, 5000, 256, 50), (129, 3001, 250, 20),
+    (300, 255, 64, 1), (300, 256, 64, 16), (257, 257, 3, 5), (64, 1000, 1, 10), (33, 2000, 257, 100),
+    (130, 7, 12, 10), (5, 1, 40, 3), (1000, 20000, 250, 128),
+])
+def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
+    rng = np.random.default_rng(nq * 1000 + nb + d + k)
+    xb = rng.standard_normal((nb, d), dtype=np.float32)
+    xq = rng.standard_normal((nq, d), dtype=np.float32)
+    D, I = _search(nf, xb, xq, k, metric, path)
+    Do, Io = oracle.knn_fast(xq, xb, k, metric)
+    rep = compare_topk(D, I, Do, Io, metric)
+    assert rep["ok"], rep
+    assert rep["recall"] == 1.0 or rep["tie_exempt_queries"] > 0
+
+
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_identity_duplicates_and_padding(nf, path):
+    d = 32
+    eye = np.eye(d, dtype=np.float32)
+    D, I = _search(nf, eye, (eye * 2)[:25], 1, 0, path)
+    assert (I[:, 0] == np.arange(25)).all() and np.allclose(D[:, 0], 2.0)
+    D, I = _search(nf, eye, (eye * 2)[:25], 1, 1, path)
+    assert (I[:, 0] == np.arange(25)).all() and np.allclose(D[:, 0], 1.0)
+    # duplicates: ids are a valid choice from the tied set, no repeats
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((50, 20), dtype=np.float32)
+    xb = np.concatenate([base, base, base])
+    xq = rng.standard_normal((30, 20), dtype=np.float32)
+    D, I = _search(nf, xb, xq, 6, 0, path)
+    for q in range(30):
+        assert len(set(I[q].tolist())) == 6
+        assert len(set((I[q, :3] % 50).tolist())) == 1 and len(set((I[q, 3:] % 50).tolist())) == 1
+    # k > ntotal: -1 / -+FLT_MAX padding
+    fmax = np.float32(3.4028234663852886e38)
+    xb = rng.standard_normal((7, 12), dtype=np.float32)
+    xq = rng.standard_normal((40, 12), dtype=np.float32)
+    for metric in (0, 1):
+        D, I = _search(nf, xb, xq, 10, metric, path)
+        assert (I[:, 7:] == -1).all() and all(sorted(r[:7].tolist()) == list(range(7)) for r in I)
+        assert (D[:, 7:] == (fmax if metric == 1 else -fmax)).all()
+
+
+def test_incremental_add_reset_and_errors(nf, oracle):
+    rng = np.random.default_rng(9)
+    xb = rng.standard_normal((3000, 250), dtype=np.float32)
+    xq = rng.standard_normal((40, 250), dtype=np.float32)
+    index = nf.IndexFlatIP(250)
+    index.add(xb[:1000])
+    index.add(xb[1000:])
+    D, I = index.search(xq, 10)
+    Do, Io = oracle.knn(xq, xb, 10, 0)
+    assert compare_topk(D, I, Do, Io, 0)["ok"]
+    assert np.array_equal(index.reconstruct_n(0, 5), xb[:5])
+    index.reset()
+    assert index.ntotal == 0
+    D, I = index.search(xq, 3)
+    assert (I == -1).all()
+    with pytest.raises(AssertionError):
+        index.search(xq[:, :10], 3)
+    with pytest.raises(AssertionError):
+        index.search(xq, 0)
+    with pytest.raises(RuntimeError):
+        index.search(xq, 1000)
+
+
+def test_cuda_tensor_in_cuda_tensor_out(nf, oracle):
+    import torch
+    rng = np.random.default_rng(10)
+    xb = rng.standard_normal((2000, 250), dtype=np.float32)
+    xq = rng.standard_normal((100, 250), dtype=np.float32)
+    index = nf.IndexFlatL2(250)
+    index.add(torch.from_numpy(xb).cuda())
+    D, I = index.search(torch.from_numpy(xq).cuda(), 5)
+    assert D.is_cuda and I.is_cuda and I.dtype == torch.int64
+    Do, Io = oracle.knn(xq, xb, 5, 1)
+    assert compare_topk(D.cpu().numpy(), I.cpu().numpy(), Do, Io, 1)["ok"]
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_midsize_skewed_catalog(nf, oracle, metric):
+    from newsrecommend_b200 import synth
+    xb, topics = synth.g_skew(60000, 250, 42, return_topics=True)
+    xq = synth.user_profiles(xb, topics, 3000, 43)
+    D, I = _search(nf, xb, xq, 50, metric, "tc")
+    Do, Io = oracle.knn_fast(xq, xb, 50, metric)
+    rep = compare_topk(D, I, Do, Io, metric)
+    assert rep["ok"], rep
+
+
+def test_full_catalog_config1_sample(nf, oracle):
+    """BASELINE config 1 catalog at full size (364,047 x 250), a 1,536-query sample against the
+    oracle, plus tcgen05-vs-SIMT agreement on a second sample."""
+    from newsrecommend_b200 import synth
+    xb, topics = synth.g_skew(synth.N_ARTICLES, 250, 42, return_topics=True)
+    xq = synth.user_profiles(xb, topics, 4096, 43)
+    index = nf.IndexFlatIP(250)
+    index.add(xb)
+    D, I = index.search(xq, 50)
+    Do, Io = oracle.knn_fast(xq[:1536], xb, 50, 0)
+    rep = compare_topk(D[:1536], I[:1536], Do, Io, 0)
+    assert rep["ok"], rep
+    assert (np.diff(D, axis=1) <= 0).all() and I.min() >= 0 and I.max() < synth.N_ARTICLES
+    index.path = PATHS["simt"]
+    Ds, Is = index.search(xq[1536:2048], 50)
+    rep = compare_topk(D[1536:2048], I[1536:2048], Ds, Is, 0)
+    assert rep["ok"], rep
+
+
+def test_item_item_cosine_self_match(nf):
+    """Config 4 shape (cosine neighbours of L2-normalised items): the self match is rank 0 with
+    score ~1 and idempotent normalisation."""
+    from newsrecommend_b200 import synth
+    x = synth.g_skew(20000, 250, 11)
+    nf.normalize_L2(x)
+    assert np.allclose((x.astype(np.float64) ** 2).sum(1), 1.0, atol=1e-5)
+    index = nf.IndexFlatIP(250)
+    index.add(x)
+    D, I = index.search(x[:4000], 20)
+    assert (I[:, 0] == np.arange(4000)).mean() > 0.999  # exact duplicates aside
+    assert np.allclose(D[:, 0], 1.0, atol=1e-5)
