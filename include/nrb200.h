@@ -61,6 +61,12 @@ int nrb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t nrb_launch_count(void);
 
+/* Device-side timing of the dominant (distance + selection) kernel: when enabled, every such
+ * launch is bracketed by CUDA events on its stream; nrb_profile_read() synchronises, returns the
+ * summed milliseconds and the launch count since the last read, and resets. */
+int nrb_profile_enable(int on);
+int nrb_profile_read(double* total_ms, int* n_launches);
+
 /* ---- K0: pack ---------------------------------------------------------------------------- */
 /* Replaces the numpy cast + contiguity at Retrieval.py:8,17,31 (and IndexFlatCodes::add's
  * memcpy, Retrieval.py:26): x is fp32 [n, d] with row stride ldx elements. Any of raw/hi/lo/

@@ -20,6 +20,7 @@ MAX_K = 128
 # every symbol include/nrb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "nrb_version", "nrb_last_error", "nrb_device_info", "nrb_launch_count",
+    "nrb_profile_enable", "nrb_profile_read",
     "nrb_pack_rows", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
     "nrb_search_flat_workspace", "nrb_search_flat",
     "nrb_kmeans_update_workspace", "nrb_kmeans_update",
@@ -50,6 +51,8 @@ lib.nrb_version.restype = C.c_int
 lib.nrb_last_error.argtypes = [C.c_char_p, C.c_int]
 lib.nrb_device_info.argtypes = [C.POINTER(C.c_int)] * 3
 lib.nrb_launch_count.restype = _i64
+lib.nrb_profile_enable.argtypes = [C.c_int]
+lib.nrb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
 lib.nrb_pack_rows.argtypes = [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]
 lib.nrb_gather_rows.argtypes = [_vp, _i32, _vp, _i64, _vp, _vp]
 lib.nrb_gather_i64.argtypes = [_vp, _vp, _i64, _vp, _vp]
@@ -83,6 +86,17 @@ def check(rc: int, what: str = "") -> int:
     if rc < 0:
         raise RuntimeError(f"libnrb200 {what} failed (code {rc}): {last_error()}")
     return rc
+
+
+def profile_enable(on: bool) -> None:
+    lib.nrb_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """(total ms, launches) of the dominant kernel since the last read."""
+    ms, n = C.c_double(0), C.c_int(0)
+    lib.nrb_profile_read(C.byref(ms), C.byref(n))
+    return ms.value, n.value
 
 
 def launch_count() -> int:

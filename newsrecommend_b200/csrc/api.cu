@@ -124,6 +124,29 @@ static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int pat
     return w;
 }
 
+// Optional device-side timing of the dominant kernel (bench.py's roofline leg): CUDA events on
+// the launching stream around every distance+selection launch.
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+struct ProfScope {
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    explicit ProfScope(cudaStream_t s) : st(s) {
+        if (!g_profile) return;
+        cudaEvent_t e0;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+            e1 = nullptr;
+            return;
+        }
+        cudaEventRecord(e0, st);
+        g_prof_events.emplace_back(e0, e1);
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
+
 static int resolve_path(int path) { return path == NRB_PATH_SIMT ? NRB_PATH_SIMT : NRB_PATH_TC; }
 
 // ------------------------------------------------------------------------------ IVF grouping
@@ -284,6 +307,30 @@ extern "C" int nrb_device_info(int* sms, int* cc_major, int* cc_minor) {
     return NRB_OK;
 }
 
+extern "C" int nrb_profile_enable(int on) {
+    g_profile = on != 0;
+    return NRB_OK;
+}
+
+extern "C" int nrb_profile_read(double* total_ms, int* n_launches) {
+    double tot = 0;
+    int n = 0;
+    for (auto& pr : g_prof_events) {
+        float ms = 0;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            tot += ms;
+            n++;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = n;
+    return NRB_OK;
+}
+
 extern "C" int64_t nrb_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp) {
@@ -316,10 +363,13 @@ extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t
         return NRB_ERR_WORKSPACE;
     }
     if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.nsplit, p.chunk_rows, st))) return rc;
-    if (path == NRB_PATH_SIMT)
-        rc = launch_topk_simt_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
-    else
-        rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    {
+        ProfScope prof(st);
+        if (path == NRB_PATH_SIMT)
+            rc = launch_topk_simt_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+        else
+            rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    }
     if (rc) return rc;
     return launch_select(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, metric, nullptr, id_base, D, I, st);
 }
@@ -393,10 +443,15 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
         g.norms = w.g_norms;
     }
     // 4. distance + selection over the units, 5. merge per query
+    ProfScope prof(st);
     if (path == NRB_PATH_SIMT)
         rc = launch_topk_simt_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
     else
         rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    if (prof.e1) {
+        cudaEventRecord(prof.e1, st);
+        prof.e1 = nullptr;
+    }
     if (rc) return rc;
     return launch_select(w.part_key, w.part_idx, w.src, nprobe * p.maxsplit, q->n, k, metric, ids, 0, D, I, st);
 }

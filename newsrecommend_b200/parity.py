@@ -5,8 +5,9 @@
   that touches position k-1 may also exchange members with items ranked beyond k, which is
   accepted when the candidate's own score is within the gap of the reference's k-th score;
 * scores must agree within `score_rtol` (1e-4) relative. For L2 the tolerance is relative to the
-  largest distance in the row as well, because a squared distance is a difference of O(|x|^2)
-  terms (a self-match has true distance 0).
+  largest distance in the row as well (or to `scale`, e.g. |q|^2 + max|x|^2, when given), because
+  faiss's and our squared distance is a difference of O(|x|^2) terms (a self-match has true
+  distance 0, and in low dimensions every near neighbour is a cancellation).
 
 Pure numpy; no oracle import -- callers pass the reference (D, I).
 """

@@ -31,7 +31,8 @@ clus.niter = 3
 trace = []
 clus.trace = lambda it, cin, a, cout: trace.append((cin.copy(), a.copy(), cout.copy()))
 clus.train(x, fo.IndexFlatL2(64))
-np.savez_compressed(os.path.join(HERE, "kmeans_small.npz"), x=x,
+xs = clus.subsample(x)  # 6000 > 20*256 -> the iterations run on the rand_perm(1234) subsample
+np.savez_compressed(os.path.join(HERE, "kmeans_small.npz"), x=x, xs=xs,
                     cin=np.stack([t[0] for t in trace]), assign=np.stack([t[1] for t in trace]),
                     cout=np.stack([t[2] for t in trace]), centroids=clus.centroids)
 print("golden fixtures written")

@@ -13,6 +13,13 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 PATHS = {"tc": 2, "simt": 1}
 
 
+def _l2_scale(xq, xb):
+    """|q|^2 + max |x|^2: the size of the terms the norm trick cancels (tolerance scale for L2)."""
+    if xb.shape[0] == 0:
+        return None
+    return (xq.astype(np.float64) ** 2).sum(1, keepdims=True) + (xb.astype(np.float64) ** 2).sum(1).max()
+
+
 def _search(nf, xb, xq, k, metric, path):
     index = nf.IndexFlatIP(xb.shape[1]) if metric == 0 else nf.IndexFlatL2(xb.shape[1])
     index.path = PATHS[path]
@@ -58,7 +65,7 @@ def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
     xq = rng.standard_normal((nq, d), dtype=np.float32)
     D, I = _search(nf, xb, xq, k, metric, path)
     Do, Io = oracle.knn_fast(xq, xb, k, metric)
-    rep = compare_topk(D, I, Do, Io, metric)
+    rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
     assert rep["ok"], rep
     assert rep["recall"] == 1.0 or rep["tie_exempt_queries"] > 0
 

@@ -53,7 +53,8 @@ def test_kmeans_teacher_forced_against_golden(nf):
     rule) and new centroids within 1e-6 relative."""
     import torch
     g = np.load(os.path.join(GOLDEN, "kmeans_small.npz"))
-    x = g["x"]
+    x = g["xs"]  # the rows the oracle iterated on (rand_perm subsample of g["x"])
+    assert np.array_equal(x, g["x"][nf.rand_perm(g["x"].shape[0], 1234)[: x.shape[0]]])
     p = nf.PackedMatrix.from_tensor(torch.from_numpy(x).cuda())
     for it in range(g["cin"].shape[0]):
         index = nf.IndexFlatL2(x.shape[1])
