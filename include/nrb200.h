@@ -61,6 +61,9 @@ int nrb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t nrb_launch_count(void);
 
+/* Selects the tcgen05 kernel variant: 2 = CTA pairs (cta_group::2, default), 1 = single CTA.
+ * Same results; kept for cross-checks and A/B timing. Also settable with NRB_TC_VARIANT=1. */
+int nrb_set_tc_variant(int v);
 /* Device-side timing of the dominant (distance + selection) kernel: when enabled, every such
  * launch is bracketed by CUDA events on its stream; nrb_profile_read() synchronises, returns the
  * summed milliseconds and the launch count since the last read, and resets. */

@@ -20,7 +20,7 @@ MAX_K = 128
 # every symbol include/nrb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "nrb_version", "nrb_last_error", "nrb_device_info", "nrb_launch_count",
-    "nrb_profile_enable", "nrb_profile_read",
+    "nrb_profile_enable", "nrb_profile_read", "nrb_set_tc_variant",
     "nrb_pack_rows", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
     "nrb_search_flat_workspace", "nrb_search_flat",
     "nrb_kmeans_update_workspace", "nrb_kmeans_update",
@@ -52,6 +52,7 @@ lib.nrb_last_error.argtypes = [C.c_char_p, C.c_int]
 lib.nrb_device_info.argtypes = [C.POINTER(C.c_int)] * 3
 lib.nrb_launch_count.restype = _i64
 lib.nrb_profile_enable.argtypes = [C.c_int]
+lib.nrb_set_tc_variant.argtypes = [C.c_int]
 lib.nrb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
 lib.nrb_pack_rows.argtypes = [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]
 lib.nrb_gather_rows.argtypes = [_vp, _i32, _vp, _i64, _vp, _vp]

@@ -82,9 +82,10 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     if (max_split < 1) max_split = 1;
     int best = 1;
     double best_eff = 0;
+    const int nqt2 = (p.nqt + 1) & ~1;
     for (int s = 1; s <= max_split; s++) {
         const double units = (double)p.nqt * s;
-        const double waves = (double)(((int64_t)p.nqt * s + sms - 1) / sms);
+        const double waves = (double)(((int64_t)nqt2 * s + sms - 1) / sms);
         const double eff = units / (waves * sms);
         if (eff > best_eff + 0.02) {
             best_eff = eff;
@@ -94,7 +95,7 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     const int tiles_per = (nbt + best - 1) / best;
     p.chunk_rows = tiles_per * tile;
     p.nsplit = (nbt + tiles_per - 1) / tiles_per;
-    p.n_units = p.nqt * p.nsplit;
+    p.n_units = ((p.nqt + 1) & ~1) * p.nsplit;  // query tiles padded to whole CTA pairs
     p.grid = path == NRB_PATH_SIMT ? simt_grid(p.n_units) : tc_grid(p.n_units);
     return p;
 }
@@ -150,8 +151,9 @@ struct ProfScope {
 static int resolve_path(int path) { return path == NRB_PATH_SIMT ? NRB_PATH_SIMT : NRB_PATH_TC; }
 
 // ------------------------------------------------------------------------------ IVF grouping
-// Single block: per list, the number of (query, list) pairs m_l, query tiles, item-run splits
-// and the first unit index; writes the unit list.
+// Single block: per list, the number of (query, list) pairs m_l, query tiles (padded to an even
+// count so that units 2p, 2p+1 share their item rows), item-run splits and the first unit
+// index; writes the unit list ordered (list, split, tile).
 __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __restrict__ l_off, int nlist,
                                 int chunk, int* __restrict__ ubase, int* __restrict__ nsl,
                                 int* __restrict__ n_units_out, Unit* __restrict__ units, int max_units) {
@@ -159,10 +161,10 @@ __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __rest
     for (int l = threadIdx.x; l < nlist; l += blockDim.x) {
         const int m = p_off[l + 1] - p_off[l];
         const int len = l_off[l + 1] - l_off[l];
-        const int tiles = (m + UNIT_ROWS - 1) / UNIT_ROWS;
+        const int tiles2 = (((m + UNIT_ROWS - 1) / UNIT_ROWS) + 1) & ~1;
         const int ns = (m > 0 && len > 0) ? (len + chunk - 1) / chunk : 0;
         nsl[l] = ns;
-        cnt[l] = tiles * ns;
+        cnt[l] = tiles2 * ns;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -173,7 +175,7 @@ __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __rest
             run += t;
         }
         cnt[nlist] = run;
-        *n_units_out = run < max_units ? run : max_units;
+        *n_units_out = run < max_units ? (run & ~1) : (max_units & ~1);
     }
     __syncthreads();
     for (int l = threadIdx.x; l <= nlist; l += blockDim.x) ubase[l] = cnt[l];
@@ -183,13 +185,14 @@ __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __rest
         const int ns = nsl[l];
         if (ns == 0) continue;
         const int tiles = (m + UNIT_ROWS - 1) / UNIT_ROWS;
+        const int tiles2 = (tiles + 1) & ~1;
         int u = cnt[l];
-        for (int t = 0; t < tiles; t++)
-            for (int s = 0; s < ns; s++, u++) {
+        for (int s = 0; s < ns; s++)
+            for (int t = 0; t < tiles2; t++, u++) {
                 if (u >= max_units) continue;
                 Unit un;
-                un.a_row0 = p_off[l] + t * UNIT_ROWS;
-                un.a_rows = min(UNIT_ROWS, m - t * UNIT_ROWS);
+                un.a_row0 = t < tiles ? p_off[l] + t * UNIT_ROWS : 0;
+                un.a_rows = t < tiles ? min(UNIT_ROWS, m - t * UNIT_ROWS) : 0;
                 un.b_row0 = l_off[l] + s * chunk;
                 un.b_rows = min(chunk, len - s * chunk);
                 units[u] = un;
@@ -206,14 +209,17 @@ __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __
          e += (int64_t)gridDim.x * blockDim.x) {
         const int pos = pos_of[e];
         const int64_t l = coarse[e];
-        int ns = 0, first = 0;
+        int ns = 0, first = 0, stride = 0;
         if (pos >= 0 && l >= 0 && l < nlist) {
             ns = nsl[l];
             const int i = pos - p_off[l];
-            first = (ubase[l] + (i / UNIT_ROWS) * ns) * UNIT_ROWS + (i % UNIT_ROWS);
+            const int m = p_off[l + 1] - p_off[l];
+            const int tiles2 = (((m + UNIT_ROWS - 1) / UNIT_ROWS) + 1) & ~1;
+            first = (ubase[l] + i / UNIT_ROWS) * UNIT_ROWS + (i % UNIT_ROWS);
+            stride = tiles2 * UNIT_ROWS;
         }
         for (int s = 0; s < maxsplit; s++)
-            src[e * maxsplit + s] = (s < ns) ? first + s * UNIT_ROWS : -1;
+            src[e * maxsplit + s] = (s < ns) ? first + s * stride : -1;
     }
 }
 
@@ -229,7 +235,7 @@ static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int
     p.npairs = nq * nprobe;
     p.maxsplit = (max_list_len + IVF_CHUNK - 1) / IVF_CHUNK;
     if (p.maxsplit < 1) p.maxsplit = 1;
-    int64_t mu = (p.npairs / UNIT_ROWS + nlist) * p.maxsplit;
+    int64_t mu = (p.npairs / UNIT_ROWS + 2 * (int64_t)nlist) * p.maxsplit;
     p.max_units = (int)mu;
     p.grid = path == NRB_PATH_SIMT ? simt_grid(p.max_units) : tc_grid(p.max_units);
     return p;
@@ -304,6 +310,12 @@ extern "C" int nrb_device_info(int* sms, int* cc_major, int* cc_minor) {
     if (sms) *sms = p.multiProcessorCount;
     if (cc_major) *cc_major = p.major;
     if (cc_minor) *cc_minor = p.minor;
+    return NRB_OK;
+}
+
+extern "C" int nrb_set_tc_variant(int v) {
+    NRB_REQUIRE(v == 1 || v == 2, "set_tc_variant: 1 (single CTA) or 2 (CTA pair)");
+    tc_set_variant(v);
     return NRB_OK;
 }
 

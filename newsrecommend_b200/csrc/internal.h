@@ -25,6 +25,7 @@ constexpr int UNIT_ROWS = 128;
 int tc_available();  // 1 when the current device is sm_100
 size_t tc_scratch_bytes(int grid);
 int tc_grid(int n_units_upper);
+void tc_set_variant(int v);  // 1 = single-CTA kernel, 2 = CTA-pair kernel (default)
 int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                        const int* n_units_dev, int grid, int metric, int k, float* part_key,
                        int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st);

@@ -343,20 +343,23 @@ __global__ void merge_kernel(const float* __restrict__ Dp, const int64_t* __rest
     }
 }
 
-// Units + src table of the flat search: unit u = s*nqt + t covers query tile t and item chunk
-// s; concurrently resident CTAs (consecutive u) share the chunk, so its tiles stay in L2.
+// Units + src table of the flat search: unit u = s*nqt2 + t covers query tile t and item chunk
+// s (nqt2 = nqt rounded up to even; the odd tile out is a phantom unit with a_rows = 0, so that
+// units 2p and 2p+1 always share their item rows -- the CTA-pair kernel needs that).
+// Concurrently resident CTAs (consecutive u) share the chunk, so its tiles stay in L2.
 __global__ void fill_flat_units_kernel(Unit* __restrict__ units, int* __restrict__ n_units_out,
                                        int* __restrict__ src, int64_t nq, int64_t nb, int nqt,
                                        int nsplit, int chunk_rows) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nunits = (int64_t)nqt * nsplit;
+    const int nqt2 = (nqt + 1) & ~1;
+    const int64_t nunits = (int64_t)nqt2 * nsplit;
     if (tid == 0) *n_units_out = (int)nunits;
     if (tid < nunits) {
-        const int s = (int)(tid / nqt), t = (int)(tid % nqt);
+        const int s = (int)(tid / nqt2), t = (int)(tid % nqt2);
         Unit u;
-        u.a_row0 = t * UNIT_ROWS;
         int64_t ar = nq - (int64_t)t * UNIT_ROWS;
-        u.a_rows = (int)(ar < UNIT_ROWS ? ar : UNIT_ROWS);
+        u.a_rows = t < nqt ? (int)(ar < UNIT_ROWS ? ar : UNIT_ROWS) : 0;
+        u.a_row0 = t < nqt ? t * UNIT_ROWS : 0;
         u.b_row0 = s * chunk_rows;
         int64_t br = nb - (int64_t)s * chunk_rows;
         u.b_rows = (int)(br < chunk_rows ? (br > 0 ? br : 0) : chunk_rows);
@@ -366,7 +369,7 @@ __global__ void fill_flat_units_kernel(Unit* __restrict__ units, int* __restrict
     for (int64_t e = tid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = e / nsplit;
         const int s = (int)(e - q * nsplit);
-        src[e] = (int)(((int64_t)s * nqt + q / UNIT_ROWS) * UNIT_ROWS + q % UNIT_ROWS);
+        src[e] = (int)(((int64_t)s * nqt2 + q / UNIT_ROWS) * UNIT_ROWS + q % UNIT_ROWS);
     }
 }
 
@@ -398,7 +401,7 @@ int launch_select(const float* part_key, const int* part_idx, const int* src, in
 int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
                            int nsplit, int chunk_rows, cudaStream_t st) {
     const int64_t total = nq * nsplit;
-    int64_t nunits = (int64_t)nqt * nsplit;
+    int64_t nunits = (int64_t)((nqt + 1) & ~1) * nsplit;
     int64_t work = total > nunits ? total : nunits;
     int blocks = (int)((work + 255) / 256);
     if (blocks > 4096) blocks = 4096;

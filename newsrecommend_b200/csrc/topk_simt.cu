@@ -37,7 +37,8 @@ topk_simt_kernel(const float* __restrict__ A, const float* __restrict__ An,
     int* ci = cand_idx_buf + (int64_t)blockIdx.x * SBM * CAND_CAP;
 
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const Unit un = units[u];
+        Unit un = units[u];
+        if (un.a_rows == 0) un.b_rows = 0;  // phantom unit (pair padding): only writes empty rows
         for (int r = tid; r < SBM; r += STHREADS) {
             sm.cnt[r] = 0;
             sm.thr[r] = (r < un.a_rows) ? NEG_INF : __builtin_huge_valf();

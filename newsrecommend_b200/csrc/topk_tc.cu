@@ -4,10 +4,10 @@
 // HeapBlockResultHandler) behind IndexFlat::search, i.e. Retrieval.py:21,32 and the assignment
 // search inside Clustering::train (Retrieval.py:18).
 //
-// One persistent CTA per SM walks a list of Units (128 query rows x a run of item rows). Per
-// 128 x 256 score tile:
+// Persistent CTAs walk a list of Units (128 query rows x a run of item rows). Per 128 x 256
+// score tile:
 //   warp 0  (1 lane)  TMA producer: hi/lo planes of the query tile and the item tile, K chunks
-//                     of 32 fp32 (128-byte swizzled rows), 2-stage mbarrier ring
+//                     of 32 fp32 (128-byte swizzled rows), mbarrier ring
 //   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
 //                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
 //   warps 2-5         epilogue: tcgen05.ld the 128 x 256 accumulator (one query row per thread),
@@ -16,7 +16,17 @@
 //                     prune brings a full buffer back to the best k and raises the threshold.
 // TMEM holds two accumulators (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of
 // tile t+1. The score matrix never exists in HBM.
+//
+// Two variants share the epilogue:
+//   v2 (default)  CTA pairs, tcgen05.mma.cta_group::2 with M = 256: the two CTAs of a cluster
+//                 take two adjacent units that share their item rows; each CTA stages its own
+//                 128 query rows and HALF of the 256-row item tile, so the item stream is read
+//                 from L2 once per 256 queries. 3 stages x 64 KB per CTA.
+//   v1            one CTA per unit, cta_group::1, M = 128; 2 stages x 96 KB. Kept as the
+//                 simpler cross-check (nrb_set_tc_variant(1)).
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "internal.h"
@@ -26,16 +36,21 @@ namespace nrb {
 
 namespace {
 
-constexpr int BM = 128;   // query rows per tile (= TMEM lanes)
+constexpr int BM = 128;   // query rows per CTA tile (= TMEM lanes)
 constexpr int BN = 256;   // item rows per tile (= TMEM columns per accumulator)
 constexpr int KC = 32;    // fp32 elements per K chunk (128-byte swizzle span)
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * KC * 4;
-constexpr int B_BYTES = BN * KC * 4;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands
+constexpr int A_BYTES = BM * KC * 4;        // 16 KB: 128 rows x 128 B
+constexpr int BH_BYTES = (BN / 2) * KC * 4; // 16 KB: half item tile (v2)
+constexpr int B_BYTES = BN * KC * 4;        // 32 KB: full item tile (v1)
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
+constexpr int V1_STAGES = 2;
+constexpr int V1_STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 96 KB
+constexpr int V2_STAGES = 3;
+constexpr int V2_STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // 64 KB
+
+template <int STAGES>
 struct TcShared {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
@@ -46,8 +61,92 @@ struct TcShared {
     float nrm[2][BN];
 };
 
-constexpr size_t TC_SMEM = (size_t)STAGES * STAGE_BYTES + sizeof(TcShared) + 1024;
+constexpr size_t V1_SMEM = (size_t)V1_STAGES * V1_STAGE_BYTES + sizeof(TcShared<V1_STAGES>) + 1024;
+constexpr size_t V2_SMEM = (size_t)V2_STAGES * V2_STAGE_BYTES + sizeof(TcShared<V2_STAGES>) + 1024;
 
+// ---------------------------------------------------------------------------- epilogue
+struct EpiRow {
+    int cnt;
+    float thr;
+    float qn;
+};
+
+// One 128 x 256 accumulator: thread = query row, 8 chunks of 32 columns.
+//   taddr0  TMEM address of (this warp's lane quarter, accumulator column 0)
+//   valid   number of valid item columns in this tile (1..256)
+//   id0     item row index of column 0
+//   nrm     item norms of the tile in shared memory (L2 only)
+//   ck/ci   candidate buffers of this warp's 32 rows; myk/myi = this lane's row
+template <bool L2>
+__device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
+                                         float* ck, int* ci, float* myk, int* myi, int k, int lane) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (c0 >= valid) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
+        ptx::tmem_ld_wait();
+        float f[32];
+        float m = NEG_INF;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            float x = __uint_as_float(v[i]);
+            if (L2) x = -fmaxf(st.qn + nrm[c0 + i] - 2.f * x, 0.f);
+            if (c0 + i >= valid) x = NEG_INF;
+            f[i] = x;
+            m = fmaxf(m, x);
+        }
+        if (m > st.thr) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                if (f[i] > st.thr) {
+                    myk[st.cnt] = f[i];
+                    myi[st.cnt] = id0 + c0 + i;
+                    st.cnt++;
+                }
+            }
+        }
+        unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int n = __shfl_sync(0xffffffffu, st.cnt, src);
+            float* rk = ck + (int64_t)src * CAND_CAP;
+            int* ri = ci + (int64_t)src * CAND_CAP;
+            const float tnew = warp_prune_row(rk, ri, n, k, rk, ri, lane);
+            if (lane == src) {
+                st.cnt = n < k ? n : k;
+                st.thr = tnew;
+            }
+        }
+    }
+}
+
+// Unit finished: best-first top-k of the warp's 32 rows into the unit's partial rows.
+__device__ __forceinline__ void epi_unit_end(const EpiRow& st, float* ck, int* ci, int u, int quad, int k,
+                                             float* part_key, int* part_idx, int lane) {
+    for (int src = 0; src < 32; src++) {
+        const int n = __shfl_sync(0xffffffffu, st.cnt, src);
+        const int64_t o = ((int64_t)u * UNIT_ROWS + quad * 32 + src) * k;
+        warp_prune_row(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, part_key + o,
+                       part_idx + o, lane);
+    }
+}
+
+template <bool L2>
+__device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
+                                                int valid, int64_t b_total, int etid) {
+    if (L2) {
+        // stage the tile's item norms; the named barrier also orders reuse of the buffer
+        for (int c = etid; c < BN; c += 128) {
+            const int64_t br = (int64_t)un.b_row0 + col_base + c;
+            nrm[c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------- v1: one CTA
 template <bool L2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -57,9 +156,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                int64_t a_total, int64_t b_total, float* __restrict__ part_key,
                int* __restrict__ part_idx, float* __restrict__ cand_key_buf,
                int* __restrict__ cand_idx_buf) {
+    constexpr int STAGES = V1_STAGES, STAGE_BYTES = V1_STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)STAGES * STAGE_BYTES);
+    TcShared<STAGES>* sh = reinterpret_cast<TcShared<STAGES>*>(smem + (size_t)STAGES * STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = *n_units_p;
@@ -95,7 +195,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit un = units[u];
-                const int ntiles = (un.b_rows + BN - 1) / BN;
+                const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
                 for (int t = 0; t < ntiles; t++) {
                     const int brow = un.b_row0 + t * BN;
                     for (int kc = 0; kc < nkc; kc++) {
@@ -124,7 +224,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit un = units[u];
-                const int ntiles = (un.b_rows + BN - 1) / BN;
+                const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
                 for (int t = 0; t < ntiles; t++) {
                     ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
                     ptx::tcgen05_fence_after();
@@ -171,82 +271,30 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const Unit un = units[u];
-            const int ntiles = (un.b_rows + BN - 1) / BN;
-            int cnt = 0;
-            float thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
-            float qn = 0.f;
+            const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
+            EpiRow st;
+            st.cnt = 0;
+            st.thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
+            st.qn = 0.f;
             if (L2) {
                 const int64_t ar = (int64_t)un.a_row0 + row;
-                qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
+                st.qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
             }
             for (int t = 0; t < ntiles; t++) {
-                const int col_base = t * BN;  // column offset inside the unit
+                const int col_base = t * BN;
                 const int valid = un.b_rows - col_base;
-                if (L2) {
-                    // stage the tile's item norms; the named barrier also orders reuse of nrm[acc]
-                    for (int c = etid; c < BN; c += 128) {
-                        const int64_t br = (int64_t)un.b_row0 + col_base + c;
-                        sh->nrm[acc][c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
+                epi_stage_norms<L2>(sh->nrm[acc], b_norms, un, col_base, valid, b_total, etid);
                 ptx::mbar_wait(&sh->tfull[acc], acc_phase);
                 ptx::tcgen05_fence_after();
                 const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    if (c0 >= valid) break;  // warp-uniform
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
-                    ptx::tmem_ld_wait();
-                    float f[32];
-                    float m = NEG_INF;
-#pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        float x = __uint_as_float(v[i]);
-                        if (L2) x = -fmaxf(qn + sh->nrm[acc][c0 + i] - 2.f * x, 0.f);
-                        if (c0 + i >= valid) x = NEG_INF;
-                        f[i] = x;
-                        m = fmaxf(m, x);
-                    }
-                    if (m > thr) {
-#pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            if (f[i] > thr) {
-                                myk[cnt] = f[i];
-                                myi[cnt] = un.b_row0 + col_base + c0 + i;
-                                cnt++;
-                            }
-                        }
-                    }
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > CAND_CAP - 32);
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int n = __shfl_sync(0xffffffffu, cnt, src);
-                        float* rk = ck + (int64_t)src * CAND_CAP;
-                        int* ri = ci + (int64_t)src * CAND_CAP;
-                        const float tnew = warp_prune_row(rk, ri, n, k, rk, ri, lane);
-                        if (lane == src) {
-                            cnt = n < k ? n : k;
-                            thr = tnew;
-                        }
-                    }
-                }
-                // accumulator drained: hand it back to the MMA warp
+                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, lane);
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&sh->tempty[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            // unit done: best-first top-k of every row into the unit's partial rows
-            for (int src = 0; src < 32; src++) {
-                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                const int64_t o = ((int64_t)u * UNIT_ROWS + quad * 32 + src) * k;
-                warp_prune_row(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k,
-                               part_key + o, part_idx + o, lane);
-            }
+            epi_unit_end(st, ck, ci, u, quad, k, part_key, part_idx, lane);
         }
     }
 
@@ -258,6 +306,177 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------- v2: CTA pairs
+// Cluster c handles unit pairs p = c, c + n_clusters, ...; CTA rank r of the pair owns unit
+// 2p + r. Both units of a pair have the same item rows (the planners guarantee it).
+template <bool L2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc, int k,
+                const float* __restrict__ a_norms, const float* __restrict__ b_norms,
+                int64_t a_total, int64_t b_total, float* __restrict__ part_key,
+                int* __restrict__ part_idx, float* __restrict__ cand_key_buf,
+                int* __restrict__ cand_idx_buf) {
+    constexpr int STAGES = V2_STAGES, STAGE_BYTES = V2_STAGE_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    TcShared<STAGES>* sh = reinterpret_cast<TcShared<STAGES>*>(smem + (size_t)STAGES * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = (*n_units_p + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&sh->full[s], 1);   // leader: its own arrive.expect_tx covers both CTAs' bytes
+            ptx::mbar_init(&sh->empty[s], 1);  // multicast tcgen05.commit from the leader
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&sh->tfull[a], 1);   // multicast tcgen05.commit from the leader
+            ptx::mbar_init(&sh->tempty[a], 8);  // leader: 4 epilogue warps of each CTA
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&map_ah);
+        ptx::prefetch_tensormap(&map_al);
+        ptx::prefetch_tensormap(&map_bh);
+        ptx::prefetch_tensormap(&map_bl);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_cg2(&sh->tmem_base, TMEM_COLS);
+        ptx::tmem_relinquish_cg2();
+    }
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    ptx::cluster_sync_all();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            uint32_t full0[STAGES];  // the leader's full barriers (shared::cluster addresses)
+            for (int s = 0; s < STAGES; s++) full0[s] = ptx::mapa_u32(&sh->full[s], 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+                const Unit un = units[2 * p + rank];
+                const int ntiles = (un.b_rows + BN - 1) / BN;
+                for (int t = 0; t < ntiles; t++) {
+                    const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);  // this CTA's half of the item tile
+                    for (int kc = 0; kc < nkc; kc++) {
+                        ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * STAGE_BYTES);
+                        ptx::tma_load_2d_cg2(st, &map_ah, full0[stage], kc * KC, un.a_row0);
+                        ptx::tma_load_2d_cg2(st + A_BYTES, &map_al, full0[stage], kc * KC, un.a_row0);
+                        ptx::tma_load_2d_cg2(st + 2 * A_BYTES, &map_bh, full0[stage], kc * KC, brow);
+                        ptx::tma_load_2d_cg2(st + 2 * A_BYTES + BH_BYTES, &map_bl, full0[stage], kc * KC, brow);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+                const Unit un = units[2 * p];
+                const int ntiles = (un.b_rows + BN - 1) / BN;
+                for (int t = 0; t < ntiles; t++) {
+                    ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kc = 0; kc < nkc; kc++) {
+                        ptx::mbar_wait(&sh->full[stage], phase);
+                        ptx::tcgen05_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                        const uint32_t s_ah = sa, s_al = sa + A_BYTES, s_bh = sa + 2 * A_BYTES,
+                                       s_bl = sa + 2 * A_BYTES + BH_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ks++) {
+                            const uint32_t off = ks * 32;
+                            const uint64_t d_ah = ptx::umma_desc_sw128(s_ah + off);
+                            const uint64_t d_al = ptx::umma_desc_sw128(s_al + off);
+                            const uint64_t d_bh = ptx::umma_desc_sw128(s_bh + off);
+                            const uint64_t d_bl = ptx::umma_desc_sw128(s_bl + off);
+                            ptx::umma_tf32_cg2(d_tmem, d_al, d_bh, idesc, (kc | ks) != 0);
+                            ptx::umma_tf32_cg2(d_tmem, d_ah, d_bl, idesc, 1);
+                            ptx::umma_tf32_cg2(d_tmem, d_ah, d_bh, idesc, 1);
+                        }
+                        ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);  // both CTAs' stage is free
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);  // both CTAs' accumulator halves complete
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ selection epilogue (both CTAs)
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int etid = (warp - 2) * 32 + lane;
+        float* ck = cand_key_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
+        int* ci = cand_idx_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
+        float* myk = ck + (int64_t)lane * CAND_CAP;
+        int* myi = ci + (int64_t)lane * CAND_CAP;
+        const uint32_t tempty0[2] = {ptx::mapa_u32(&sh->tempty[0], 0), ptx::mapa_u32(&sh->tempty[1], 0)};
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+            const int u = 2 * p + (int)rank;
+            const Unit un = units[u];
+            const int ntiles = (un.b_rows + BN - 1) / BN;
+            EpiRow st;
+            st.cnt = 0;
+            st.thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
+            st.qn = 0.f;
+            if (L2) {
+                const int64_t ar = (int64_t)un.a_row0 + row;
+                st.qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
+            }
+            for (int t = 0; t < ntiles; t++) {
+                const int col_base = t * BN;
+                const int valid = un.b_rows - col_base;
+                epi_stage_norms<L2>(sh->nrm[acc], b_norms, un, col_base, valid, b_total, etid);
+                ptx::mbar_wait(&sh->tfull[acc], acc_phase);
+                ptx::tcgen05_fence_after();
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, lane);
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(tempty0[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            epi_unit_end(st, ck, ci, u, quad, k, part_key, part_idx, lane);
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    ptx::cluster_sync_all();  // both CTAs are done with the pair's TMEM and barriers
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -297,6 +516,16 @@ int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int kp, int 
     return NRB_OK;
 }
 
+int g_variant = 0;  // 0 = not yet read from the environment
+
+int variant() {
+    if (g_variant == 0) {
+        const char* e = getenv("NRB_TC_VARIANT");
+        g_variant = (e && e[0] == '1') ? 1 : 2;
+    }
+    return g_variant;
+}
+
 }  // namespace
 
 int tc_available() {
@@ -307,10 +536,13 @@ int tc_available() {
     return p.major == 10 ? 1 : 0;
 }
 
+void tc_set_variant(int v) { g_variant = (v == 1) ? 1 : 2; }
+
 int tc_grid(int n_units) {
-    int g = sm_count();
-    if (n_units > 0 && n_units < g) g = n_units;
-    return g < 1 ? 1 : g;
+    int g = sm_count() & ~1;  // whole CTA pairs
+    int need = (n_units + 1) & ~1;
+    if (need > 0 && need < g) g = need;
+    return g < 2 ? 2 : g;
 }
 
 size_t tc_scratch_bytes(int grid) {
@@ -324,30 +556,39 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
     NRB_REQUIRE(a->kp == b->kp && a->kp % KC == 0 && a->kp >= KC, "tc: kp mismatch / not a multiple of %d", KC);
     NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "tc: k=%d out of range [1,%d]", k, NRB_MAX_K);
     NRB_REQUIRE(metric != NRB_METRIC_L2 || (a->norms && b->norms), "tc: norms required for L2");
+    NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc: grid must be a positive even number");
     if (scratch_bytes < tc_scratch_bytes(grid)) {
         set_error("tc: scratch too small");
         return NRB_ERR_WORKSPACE;
     }
+    const int v = variant();
     CUtensorMap mah, mal, mbh, mbl;
     int rc;
     if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
     if ((rc = make_plane_map(&mal, a->lo, a->n, a->kp, BM))) return rc;
-    if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN))) return rc;
-    if ((rc = make_plane_map(&mbl, b->lo, b->n, b->kp, BN))) return rc;
+    if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, v == 1 ? BN : BN / 2))) return rc;
+    if ((rc = make_plane_map(&mbl, b->lo, b->n, b->kp, v == 1 ? BN : BN / 2))) return rc;
     float* ck = (float*)scratch;
     int* ci = (int*)((char*)scratch + (size_t)grid * BM * CAND_CAP * sizeof(float));
     const int nkc = a->kp / KC;
-    if (metric == NRB_METRIC_L2) {
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        topk_tc_kernel<true><<<grid, NUM_THREADS, TC_SMEM, st>>>(mah, mal, mbh, mbl, units, n_units_dev, nkc, k,
-                                                                 a->norms, b->norms, a->n, b->n, part_key,
-                                                                 part_idx, ck, ci);
+#define NRB_TC_LAUNCH(KERNEL, SMEM)                                                                          \
+    do {                                                                                                     \
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+        KERNEL<<<grid, NUM_THREADS, SMEM, st>>>(mah, mal, mbh, mbl, units, n_units_dev, nkc, k, a->norms,     \
+                                                b->norms, a->n, b->n, part_key, part_idx, ck, ci);           \
+    } while (0)
+    if (v == 1) {
+        if (metric == NRB_METRIC_L2)
+            NRB_TC_LAUNCH(topk_tc_kernel<true>, V1_SMEM);
+        else
+            NRB_TC_LAUNCH(topk_tc_kernel<false>, V1_SMEM);
     } else {
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        topk_tc_kernel<false><<<grid, NUM_THREADS, TC_SMEM, st>>>(mah, mal, mbh, mbl, units, n_units_dev, nkc, k,
-                                                                  a->norms, b->norms, a->n, b->n, part_key,
-                                                                  part_idx, ck, ci);
+        if (metric == NRB_METRIC_L2)
+            NRB_TC_LAUNCH(topk_tc2_kernel<true>, V2_SMEM);
+        else
+            NRB_TC_LAUNCH(topk_tc2_kernel<false>, V2_SMEM);
     }
+#undef NRB_TC_LAUNCH
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

@@ -175,3 +175,23 @@ def test_item_item_cosine_self_match(nf):
     D, I = index.search(x[:4000], 20)
     assert (I[:, 0] == np.arange(4000)).mean() > 0.999  # exact duplicates aside
     assert np.allclose(D[:, 0], 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_tc_kernel_variants(nf, oracle, variant, metric):
+    """Both tcgen05 kernels (1 = single CTA, 2 = CTA pair / cta_group::2) against the oracle on
+    shapes with odd query-tile counts, partial item tiles and several item chunks."""
+    from newsrecommend_b200._lib import lib
+    rng = np.random.default_rng(77 + metric)
+    try:
+        assert lib.nrb_set_tc_variant(variant) == 0
+        for nq, nb, d, k in ((48, 2000, 250, 10), (385, 30011, 250, 50), (1, 70000, 96, 7), (129, 513, 32, 128)):
+            xb = rng.standard_normal((nb, d), dtype=np.float32)
+            xq = rng.standard_normal((nq, d), dtype=np.float32)
+            D, I = _search(nf, xb, xq, k, metric, "tc")
+            Do, Io = oracle.knn_fast(xq, xb, k, metric)
+            rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
+            assert rep["ok"], (variant, nq, nb, d, k, rep)
+    finally:
+        lib.nrb_set_tc_variant(2)
