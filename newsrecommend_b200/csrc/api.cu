@@ -37,8 +37,9 @@ int sm_count() {
 }
 
 static int require_device() {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    static int n = -1;
+    if (n <= 0 && (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)) {
+        n = 0;
         cudaGetLastError();
         set_error("no CUDA device: libnrb200 has no CPU fallback");
         return NRB_ERR_NO_DEVICE;

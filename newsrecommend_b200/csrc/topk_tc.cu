@@ -529,11 +529,15 @@ int variant() {
 }  // namespace
 
 int tc_available() {
+    // cudaGetDeviceProperties costs milliseconds: query the one attribute, once per device.
+    static int cached[64] = {0};  // 0 unknown, 1 yes, -1 no
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-    return p.major == 10 ? 1 : 0;
+    if (dev >= 0 && dev < 64 && cached[dev] != 0) return cached[dev] > 0;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64) cached[dev] = major == 10 ? 1 : -1;
+    return major == 10 ? 1 : 0;
 }
 
 void tc_set_variant(int v) { g_variant = (v == 1) ? 1 : 2; }

@@ -71,11 +71,12 @@ class ShardedIndexFlat:
         """all-gather of the per-shard results -> [G, nq, k] on every rank."""
         if self.world == 1:
             return D.unsqueeze(0), I.unsqueeze(0)
-        Dp = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-        Ip = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        nq, k = D.shape
+        Dp = torch.empty((self.world * nq, k), dtype=D.dtype, device=D.device)
+        Ip = torch.empty((self.world * nq, k), dtype=I.dtype, device=I.device)
         dist.all_gather_into_tensor(Dp, D.contiguous(), group=self.group)
         dist.all_gather_into_tensor(Ip, I.contiguous(), group=self.group)
-        return Dp, Ip
+        return Dp.view(self.world, nq, k), Ip.view(self.world, nq, k)
 
     def search(self, q, k: int):
         D, I = self.search_local(q, k)
