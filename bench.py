@@ -106,11 +106,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs must use every host core they can."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)  # OpenBLAS behind numpy (the sgemm blocks)
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # the oracle's OpenMP loops
+    except Exception:  # noqa: BLE001
+        pass
+    return cores
+
+
 def cpu_baseline(xb, xq, budget_s=12.0):
     """faiss-equivalent oracle port on the host cores, bounded sample of the same workload."""
     from oracle import faiss_oracle as fo
     fo.build()
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_threads()
     fo.knn_fast(xq[:512], xb, K, 0)  # warm-up (thread pools, page-in)
     t0 = time.perf_counter()
     fo.knn_fast(xq[:2048], xb, K, 0)
@@ -132,7 +148,7 @@ def run_reference(args):
     from oracle import faiss_oracle as fo
     fo.build()
     xb, xq = make_data()
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_threads()
     fo.knn_fast(xq[:512], xb, K, 0)
     t0 = time.perf_counter()
     fo.knn_fast(xq[:2048], xb, K, 0)

@@ -77,8 +77,7 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     const int tile = 256;
     int nbt = (int)((nb + tile - 1) / tile);
     if (nbt < 1) nbt = 1;
-    int max_split = 8192 / k;
-    if (max_split > 64) max_split = 64;
+    int max_split = 64;  // sources per query in the k-way merge
     if (max_split > nbt) max_split = nbt;
     if (max_split < 1) max_split = 1;
     int best = 1;
@@ -414,7 +413,7 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     cudaStream_t st = (cudaStream_t)stream;
     path = resolve_path(path);
     const IvfPlan p = plan_ivf(q->n, nprobe, nlist, max_list_len, path);
-    NRB_REQUIRE((int64_t)nprobe * p.maxsplit * k <= 16384, "ivf_search: nprobe*splits*k too large");
+    NRB_REQUIRE((int64_t)nprobe * p.maxsplit <= 256, "ivf_search: nprobe*splits = %d > 256 merge sources", nprobe * p.maxsplit);
     const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path);
     if (!workspace || workspace_bytes < w.total) {
         set_error("ivf_search: workspace %zu < %zu bytes", workspace_bytes, w.total);

@@ -235,110 +235,133 @@ __global__ void kmeans_update_kernel(const float* __restrict__ x_raw, int kp, in
 }
 
 // ------------------------------------------------------------------- select / merge (K4)
-// Block per query. Gathers S partial rows of k best-first candidates, sorts (key desc, idx
-// asc) with a shared-memory bitonic network and writes the k best.
-__global__ void select_kernel(const float* __restrict__ part_key, const int* __restrict__ part_idx,
-                              const int* __restrict__ src, int S, int k, int P /*pow2 >= S*k*/,
-                              int metric, const int64_t* __restrict__ id_map, int64_t id_base,
-                              float* __restrict__ D, int64_t* __restrict__ I) {
-    extern __shared__ uint64_t sc[];
-    const int64_t q = blockIdx.x;
-    const int total = S * k;
-    for (int e = threadIdx.x; e < P; e += blockDim.x) {
-        uint64_t c = empty_cand();
-        if (e < total) {
-            const int s = e / k, j = e - s * k;
-            const int prow = src[q * S + s];
-            if (prow >= 0) {
-                const int64_t o = (int64_t)prow * k + j;
-                const int idx = part_idx[o];
-                if (idx >= 0) c = pack_cand(part_key[o], idx);
-            }
-        }
-        sc[e] = c;
+// Every source list (a unit's partial row, or a shard's result row) is already best-first, so
+// the final top-k is a k-way merge: one warp per query, lane l owns sources l, l+32, ...;
+// each round the warp takes the best head (64-bit (key, idx) max via shuffles) and the owning
+// lane advances that list. Results are parked in registers (result r in lane r%32) and written
+// coalesced.
+struct PartSource {  // partial rows produced by the distance+selection kernels
+    const float* key;
+    const int* idx;
+    const int* src;  // [nq, S] partial row per (query, source) or -1
+    int S, k;
+    __device__ __forceinline__ int row(int64_t q, int s) const { return src[q * S + s]; }
+    __device__ __forceinline__ uint64_t load(int64_t, int, int prow, int pos) const {
+        const int64_t o = (int64_t)prow * k + pos;
+        const int i = idx[o];
+        return i >= 0 ? pack_cand(key[o], i) : empty_cand();
     }
-    __syncthreads();
-    for (int k2 = 2; k2 <= P; k2 <<= 1) {
-        for (int j = k2 >> 1; j >= 1; j >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                const int e = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower element of the pair
-                const int p = e | j;
-                const bool desc = ((e & k2) == 0);
-                const uint64_t a = sc[e], b = sc[p];
-                if ((a < b) == desc) {
-                    sc[e] = b;
-                    sc[p] = a;
+};
+struct ShardSource {  // per-shard final results [G, nq, k] with 64-bit ids (K4)
+    const float* Dp;
+    const int64_t* Ip;
+    int64_t nq;
+    int S, k, metric;
+    __device__ __forceinline__ int row(int64_t, int s) const { return s; }
+    __device__ __forceinline__ uint64_t load(int64_t q, int s, int, int pos) const {
+        const int64_t o = ((int64_t)s * nq + q) * k + pos;
+        if (Ip[o] < 0) return empty_cand();
+        const float d = Dp[o];
+        // the idx slot carries (source, position): ties between shards resolve by shard order,
+        // which is ascending id order for a row-sharded catalog
+        return pack_cand(metric == NRB_METRIC_L2 ? -d : d, s * k + pos);
+    }
+};
+
+template <int MAXL, typename Source>
+__device__ __forceinline__ void warp_kway_merge(const Source& S, int64_t q, int k, int lane,
+                                                uint64_t (&res)[4]) {
+    uint64_t head[MAXL];
+    int prow[MAXL], pos[MAXL];
+#pragma unroll
+    for (int j = 0; j < MAXL; j++) {
+        const int s = lane + 32 * j;
+        prow[j] = s < S.S ? S.row(q, s) : -1;
+        pos[j] = 0;
+        head[j] = prow[j] >= 0 ? S.load(q, s, prow[j], 0) : empty_cand();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) res[i] = empty_cand();
+    const uint64_t EMPTY = empty_cand();
+    for (int r = 0; r < k; r++) {
+        uint64_t best = head[0];
+#pragma unroll
+        for (int j = 1; j < MAXL; j++) best = head[j] > best ? head[j] : best;
+        uint64_t w = best;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const uint64_t t = shfl_xor_u64(w, o);
+            w = t > w ? t : w;
+        }
+        if (w == EMPTY) break;  // every list exhausted (warp-uniform)
+        const unsigned owners = __ballot_sync(0xffffffffu, best == w);
+        const int owner = __ffs(owners) - 1;
+        if (lane == (r & 31)) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i == (r >> 5)) res[i] = w;
+        }
+        if (lane == owner) {
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < MAXL; j++) {
+                if (!done && head[j] == w) {
+                    done = true;
+                    pos[j]++;
+                    head[j] = pos[j] < k ? S.load(q, lane + 32 * j, prow[j], pos[j]) : EMPTY;
                 }
             }
-            __syncthreads();
         }
-    }
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const uint64_t c = sc[j];
-        const int idx = cand_idx(c);
-        float key = cand_key(c);
-        int64_t id;
-        float dv;
-        if (idx < 0) {
-            id = -1;
-            dv = (metric == NRB_METRIC_L2) ? FLT_MAX : -FLT_MAX;
-        } else {
-            id = id_map ? id_map[idx] : (int64_t)idx + id_base;
-            dv = (metric == NRB_METRIC_L2) ? -key : key;
-        }
-        D[q * k + j] = dv;
-        I[q * k + j] = id;
     }
 }
 
-// k-way merge of per-shard (D, I): same network, keys from D, 64-bit ids carried by position.
-__global__ void merge_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip,
-                             int nparts, int64_t nq, int k, int P, int metric,
-                             float* __restrict__ D, int64_t* __restrict__ I) {
-    extern __shared__ uint64_t sc[];
-    const int64_t q = blockIdx.x;
-    const int total = nparts * k;
-    for (int e = threadIdx.x; e < P; e += blockDim.x) {
-        uint64_t c = empty_cand();
-        if (e < total) {
-            const int s = e / k, j = e - s * k;
-            const int64_t o = ((int64_t)s * nq + q) * k + j;
-            if (Ip[o] >= 0) {
-                const float d = Dp[o];
-                // idx slot carries the position e; ties between shards resolve by shard order,
-                // which is ascending id order for a row-sharded catalog.
-                c = pack_cand(metric == NRB_METRIC_L2 ? -d : d, e);
+template <int MAXL>
+__global__ void select_merge_kernel(PartSource S, int64_t nq, int metric,
+                                    const int64_t* __restrict__ id_map, int64_t id_base,
+                                    float* __restrict__ D, int64_t* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    uint64_t res[4];
+    warp_kway_merge<MAXL>(S, q, S.k, lane, res);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = i * 32 + lane;
+        if (r < S.k) {
+            const int idx = cand_idx(res[i]);
+            const float key = cand_key(res[i]);
+            if (idx < 0) {
+                I[q * S.k + r] = -1;
+                D[q * S.k + r] = (metric == NRB_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+            } else {
+                I[q * S.k + r] = id_map ? id_map[idx] : (int64_t)idx + id_base;
+                D[q * S.k + r] = (metric == NRB_METRIC_L2) ? -key : key;
             }
         }
-        sc[e] = c;
     }
-    __syncthreads();
-    for (int k2 = 2; k2 <= P; k2 <<= 1) {
-        for (int j = k2 >> 1; j >= 1; j >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                const int e = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = e | j;
-                const bool desc = ((e & k2) == 0);
-                const uint64_t a = sc[e], b = sc[p];
-                if ((a < b) == desc) {
-                    sc[e] = b;
-                    sc[p] = a;
-                }
+}
+
+template <int MAXL>
+__global__ void shard_merge_kernel(ShardSource S, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= S.nq) return;
+    uint64_t res[4];
+    warp_kway_merge<MAXL>(S, q, S.k, lane, res);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = i * 32 + lane;
+        if (r < S.k) {
+            const int e = cand_idx(res[i]);
+            if (e < 0) {
+                I[q * S.k + r] = -1;
+                D[q * S.k + r] = (S.metric == NRB_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+            } else {
+                const int s = e / S.k, pos = e - s * S.k;
+                const int64_t o = ((int64_t)s * S.nq + q) * S.k + pos;
+                I[q * S.k + r] = S.Ip[o];
+                D[q * S.k + r] = S.Dp[o];
             }
-            __syncthreads();
-        }
-    }
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const uint64_t c = sc[j];
-        const int e = cand_idx(c);
-        if (e < 0) {
-            I[q * k + j] = -1;
-            D[q * k + j] = (metric == NRB_METRIC_L2) ? FLT_MAX : -FLT_MAX;
-        } else {
-            const int s = e / k, jj = e - s * k;
-            const int64_t o = ((int64_t)s * nq + q) * k + jj;
-            I[q * k + j] = Ip[o];
-            D[q * k + j] = Dp[o];
         }
     }
 }
@@ -374,26 +397,22 @@ __global__ void fill_flat_units_kernel(Unit* __restrict__ units, int* __restrict
 }
 
 // ------------------------------------------------------------------- host launchers
-static int pow2_ge(int x) {
-    int p = 2;
-    while (p < x) p <<= 1;
-    return p;
-}
-
 int launch_select(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
                   int k, int metric, const int64_t* id_map, int64_t id_base, float* D, int64_t* I,
                   cudaStream_t st) {
     if (nq == 0) return NRB_OK;
-    const int P = pow2_ge(S * k);
-    NRB_REQUIRE(P <= 16384, "select: S*k = %d too large", S * k);
-    const size_t smem = (size_t)P * sizeof(uint64_t);
-    if (smem > 48 * 1024)
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(select_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = P / 2;
-    threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
-    select_kernel<<<(unsigned)nq, threads, smem, st>>>(part_key, part_idx, src, S, k, P, metric,
-                                                       id_map, id_base, D, I);
+    NRB_REQUIRE(S >= 1 && S <= 256 && k >= 1 && k <= 128, "select: S=%d (<=256) k=%d (<=128)", S, k);
+    PartSource ps{part_key, part_idx, src, S, k};
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((nq + wpb - 1) / wpb);
+    if (S <= 32)
+        select_merge_kernel<1><<<blocks, wpb * 32, 0, st>>>(ps, nq, metric, id_map, id_base, D, I);
+    else if (S <= 64)
+        select_merge_kernel<2><<<blocks, wpb * 32, 0, st>>>(ps, nq, metric, id_map, id_base, D, I);
+    else if (S <= 128)
+        select_merge_kernel<4><<<blocks, wpb * 32, 0, st>>>(ps, nq, metric, id_map, id_base, D, I);
+    else
+        select_merge_kernel<8><<<blocks, wpb * 32, 0, st>>>(ps, nq, metric, id_map, id_base, D, I);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }
@@ -552,16 +571,21 @@ extern "C" int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32
 
 extern "C" int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts, int64_t nq,
                               int32_t k, int32_t metric, float* D, int64_t* I, void* stream) {
-    NRB_REQUIRE(nparts > 0 && nq >= 0 && k > 0, "merge_topk: bad sizes");
+    NRB_REQUIRE(nparts > 0 && nparts <= 256 && nq >= 0 && k > 0 && k <= 128, "merge_topk: bad sizes");
+    NRB_REQUIRE((int64_t)nparts * k < (1LL << 31), "merge_topk: nparts*k too large");
     if (nq == 0) return NRB_OK;
-    const int P = pow2_ge(nparts * k);
-    NRB_REQUIRE(P <= 16384, "merge_topk: nparts*k = %d too large", nparts * k);
-    const size_t smem = (size_t)P * sizeof(uint64_t);
-    if (smem > 48 * 1024)
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = P / 2;
-    threads = threads < 32 ? 32 : (threads > 512 ? 512 : threads);
-    merge_kernel<<<(unsigned)nq, threads, smem, (cudaStream_t)stream>>>(Dp, Ip, nparts, nq, k, P, metric, D, I);
+    ShardSource ss{Dp, Ip, nq, nparts, k, metric};
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((nq + wpb - 1) / wpb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nparts <= 32)
+        shard_merge_kernel<1><<<blocks, wpb * 32, 0, st>>>(ss, D, I);
+    else if (nparts <= 64)
+        shard_merge_kernel<2><<<blocks, wpb * 32, 0, st>>>(ss, D, I);
+    else if (nparts <= 128)
+        shard_merge_kernel<4><<<blocks, wpb * 32, 0, st>>>(ss, D, I);
+    else
+        shard_merge_kernel<8><<<blocks, wpb * 32, 0, st>>>(ss, D, I);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }
