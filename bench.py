@@ -197,7 +197,9 @@ def run_ours(args):
     index.add_global(xb)
     xq_dev = torch.from_numpy(xq).cuda()
     xq_pin = torch.from_numpy(xq).pin_memory()
-    planes = ("hi", "lo")
+    index.local.path = {"auto": _lib.PATH_AUTO, "tc": _lib.PATH_TC, "tc1": _lib.PATH_TC1}[args.path]
+    planes = index.local._query_planes()
+    one_pass = args.path in ("auto", "tc1")
 
     def step_device():
         q = nf.PackedMatrix.from_tensor(xq_dev, planes=planes)  # K0 on the fresh query batch
@@ -264,14 +266,17 @@ def run_ours(args):
         kavg_s = kern_ms / max(1, kern_n) / 1e3
         achieved = alg / kavg_s / 1e12 if kavg_s > 0 else 0.0
         tf32_peak = pk["tf32_sustained"]
-        peak = tf32_peak / 3.0  # fp32-faithful ceiling: three TF32 passes per product
+        passes = 1.0 if one_pass else 3.0
+        peak = tf32_peak / passes
         roof = {
-            "bound": "tensor", "kernel": "topk_tc_kernel<IP> (tcgen05 3xTF32 + fused selection)",
+            "bound": "tensor",
+            "kernel": ("topk_tc3_kernel<IP> (tcgen05 1xTF32 filter with error margin; exact fp32 refine follows)"
+                       if one_pass else "topk_tc2_kernel<IP> (tcgen05 3xTF32 + fused selection)"),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_note": ("peak = cuBLAS TF32 sustained %.1f TFLOP/s (scripts/gpu_probe.py, same method as "
-                          "MEASURED_PEAKS.json; profiles/r01_probe.json) / 3 passes of 3xTF32; MEASURED_PEAKS (%s) bf16 "
-                          "sustained %.1f" % (tf32_peak, pk["src"], pk["bf16_sustained"])),
-            "tensor_pipe_frac": achieved * 3.0 * 256.0 / 250.0 / tf32_peak,
+                          "MEASURED_PEAKS.json; profiles/r01_probe.json) / %d TF32 pass(es) per product; "
+                          "MEASURED_PEAKS (%s) bf16 sustained %.1f" % (tf32_peak, int(passes), pk["src"], pk["bf16_sustained"])),
+            "tensor_pipe_frac": achieved * passes * 256.0 / 250.0 / tf32_peak,
             "frac_of_bf16_peak": achieved / pk["bf16_sustained"],
             "kernel_ms_avg": kavg_s * 1e3, "kernel_launches_timed": kern_n,
             "alg_flop_per_launch": alg,
@@ -286,11 +291,14 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 tcgen05, fp32 accumulate)",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": ("f32 (1xTF32 tcgen05 filter + exact fp32 rescoring)" if one_pass
+                      else "f32 (3xTF32 tcgen05, fp32 accumulate)"),
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "k": K, "parallelism": f"catalog row-sharded over {world} GPU(s)",
                        "l2": "inputs larger than L2 (catalog hi+lo planes 746 MB per full catalog)",
-                       "timed": "K0 query split + K2 tcgen05 distance/selection + select" +
+                       "path": args.path, "fallback_queries": int(_lib.lib.nrb_fallback_query_count()),
+                       "timed": "K0 query split + K2 tcgen05 distance/selection + select" + (" + exact refine" if one_pass else "") +
                                 (" + NCCL all-gather + K4 merge" if world > 1 else "")},
             "roofline": roof,
             "e2e": {"value": NQ * args.steps / e2e_s, "unit": "queries/s",
@@ -313,6 +321,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="auto", choices=["auto", "tc", "tc1"],
+                    help="auto/tc1 = 1xTF32 filter + exact refine (default), tc = 3xTF32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -33,6 +33,8 @@ extern "C" {
 #define NRB_PATH_AUTO 0
 #define NRB_PATH_SIMT 1 /* fp32 CUDA-core kernels */
 #define NRB_PATH_TC 2   /* tcgen05 3xTF32 kernels */
+#define NRB_PATH_TC1 3  /* tcgen05 1xTF32 filter with a rigorous error margin + exact fp32 refine;
+                           flat search only, rows that overflow the margin set fall back to TC */
 
 #define NRB_MAX_K 128 /* largest k / nprobe supported by the selection stage */
 
@@ -50,6 +52,9 @@ typedef struct nrb_matrix {
     int64_t n;
     int32_t d;
     int32_t kp;
+    float max_norm; /* max row L2 norm (not squared) over the matrix, 0 = unknown; needed on the
+                       item side by NRB_PATH_TC1 */
+    int32_t reserved;
 } nrb_matrix;
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
@@ -89,11 +94,18 @@ int nrb_normalize_l2(float* x, int64_t n, int32_t d, int64_t ldx, void* stream);
 /* Replaces IndexFlatL2/IndexFlatIP.search at Retrieval.py:21,32 and the k-means assignment
  * search inside Clustering::train (Retrieval.py:18). D f32[nq,k] best-first (IP descending,
  * L2 ascending squared distance clamped at 0), I i64[nq,k] = row index + id_base; missing
- * results are I = -1, D = -FLT_MAX (IP) / +FLT_MAX (L2). 1 <= k <= NRB_MAX_K. */
+ * results are I = -1, D = -FLT_MAX (IP) / +FLT_MAX (L2). 1 <= k <= NRB_MAX_K.
+ * path: NRB_PATH_AUTO picks NRB_PATH_TC1 when its preconditions hold (raw + hi + norms planes on
+ * both sides, b->max_norm, kp <= 256, k <= 96), else NRB_PATH_TC. NRB_PATH_TC1 synchronises the
+ * stream once per call (it reads back the number of flagged queries). */
 size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp);
 int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
                     int64_t id_base, float* D, int64_t* I, void* workspace,
                     size_t workspace_bytes, int32_t path, void* stream);
+
+/* Queries that NRB_PATH_TC1 had to recompute with the 3xTF32 kernel since the library was loaded
+ * (candidate slots exhausted inside the error margin, or an estimate outside its bound). */
+int64_t nrb_fallback_query_count(void);
 
 /* ---- K1b: k-means centroid update (Clustering.cpp compute_centroids) ---------------------- */
 /* Replaces the update step of clustering.train (Retrieval.py:18). x_raw is the packed raw

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libnrb200.so")
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
-PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1 = 0, 1, 2, 3
 MAX_K = 128
 
 # every symbol include/nrb200.h declares (tests check the library exports all of them)
@@ -22,7 +22,7 @@ SYMBOLS = [
     "nrb_version", "nrb_last_error", "nrb_device_info", "nrb_launch_count",
     "nrb_profile_enable", "nrb_profile_read", "nrb_set_tc_variant",
     "nrb_pack_rows", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
-    "nrb_search_flat_workspace", "nrb_search_flat",
+    "nrb_search_flat_workspace", "nrb_search_flat", "nrb_fallback_query_count",
     "nrb_kmeans_update_workspace", "nrb_kmeans_update",
     "nrb_rand_perm_host", "nrb_split_clusters_host",
     "nrb_ivf_build_lists_workspace", "nrb_ivf_build_lists",
@@ -34,7 +34,8 @@ SYMBOLS = [
 class Matrix(C.Structure):
     """struct nrb_matrix"""
     _fields_ = [("raw", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p), ("norms", C.c_void_p),
-                ("n", C.c_int64), ("d", C.c_int32), ("kp", C.c_int32)]
+                ("n", C.c_int64), ("d", C.c_int32), ("kp", C.c_int32), ("max_norm", C.c_float),
+                ("reserved", C.c_int32)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -61,6 +62,7 @@ lib.nrb_normalize_l2.argtypes = [_vp, _i64, _i32, _i64, _vp]
 lib.nrb_search_flat_workspace.restype = _sz
 lib.nrb_search_flat_workspace.argtypes = [_i64, _i64, _i32, _i32]
 lib.nrb_search_flat.argtypes = [_mp, _mp, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _i32, _vp]
+lib.nrb_fallback_query_count.restype = _i64
 lib.nrb_kmeans_update_workspace.restype = _sz
 lib.nrb_kmeans_update_workspace.argtypes = [_i64, _i32]
 lib.nrb_kmeans_update.argtypes = [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]

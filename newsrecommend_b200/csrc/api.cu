@@ -106,6 +106,7 @@ struct FlatWs {
     int* src;
     float* part_key;
     int* part_idx;
+    int *flags, *flag_list, *flag_count;  // NRB_PATH_TC1 only
     void* scratch;
     size_t scratch_bytes;
     size_t total;
@@ -114,11 +115,18 @@ struct FlatWs {
 static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int path) {
     Carver c(ws);
     FlatWs w;
+    const int pw = path == NRB_PATH_TC1 ? k + TC1_EXTRA : k;  // partial row width
     w.units = c.take<Unit>(p.n_units);
     w.n_units = c.take<int>(1);
     w.src = c.take<int>((size_t)nq * p.nsplit);
-    w.part_key = c.take<float>((size_t)p.n_units * UNIT_ROWS * k);
-    w.part_idx = c.take<int>((size_t)p.n_units * UNIT_ROWS * k);
+    w.part_key = c.take<float>((size_t)p.n_units * UNIT_ROWS * pw);
+    w.part_idx = c.take<int>((size_t)p.n_units * UNIT_ROWS * pw);
+    w.flags = w.flag_list = w.flag_count = nullptr;
+    if (path == NRB_PATH_TC1) {
+        w.flags = c.take<int>(nq);
+        w.flag_list = c.take<int>(nq);
+        w.flag_count = c.take<int>(1);
+    }
     w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(p.grid) : tc_scratch_bytes(p.grid);
     w.scratch = c.take<char>(w.scratch_bytes);
     w.total = c.off;
@@ -149,6 +157,8 @@ struct ProfScope {
 };
 
 static int resolve_path(int path) { return path == NRB_PATH_SIMT ? NRB_PATH_SIMT : NRB_PATH_TC; }
+
+static std::atomic<long long> g_fallback_queries{0};
 
 // ------------------------------------------------------------------------------ IVF grouping
 // Single block: per list, the number of (query, list) pairs m_l, query tiles (padded to an even
@@ -223,7 +233,7 @@ __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __
     }
 }
 
-constexpr int IVF_CHUNK = 2048;  // item rows per unit inside one list
+constexpr int IVF_CHUNK = 8192;  // item rows per unit inside one list (long runs amortise the per-unit prunes)
 
 struct IvfPlan {
     int64_t npairs;
@@ -348,12 +358,96 @@ extern "C" int64_t nrb_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp) {
     (void)kp;
     if (nq <= 0 || k <= 0 || k > NRB_MAX_K) return 256;
-    // the SIMT plan uses the wider grid; take the larger of both so `path` can be chosen per call
-    FlatPlan p1 = plan_flat(nq, nb, k, NRB_PATH_TC), p2 = plan_flat(nq, nb, k, NRB_PATH_SIMT);
-    size_t a = carve_flat(nullptr, p1, nq, k, NRB_PATH_TC).total;
-    size_t b = carve_flat(nullptr, p2, nq, k, NRB_PATH_SIMT).total;
-    return (a > b ? a : b) + 256;
+    // take the largest over the paths so that `path` can be chosen per call
+    size_t best = 0;
+    for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC1}) {
+        if (path == NRB_PATH_TC1 && k + TC1_EXTRA > 128) continue;
+        FlatPlan p = plan_flat(nq, nb, k, path);
+        size_t t = carve_flat(nullptr, p, nq, k, path).total;
+        best = t > best ? t : best;
+    }
+    return best + 256;
 }
+
+namespace nrb {
+
+static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric, int k, int64_t id_base,
+                            float* D, int64_t* I, void* workspace, size_t workspace_bytes, int path,
+                            cudaStream_t st) {
+    if (path == NRB_PATH_AUTO) path = tc1_eligible(q, b, k) ? NRB_PATH_TC1 : NRB_PATH_TC;
+    if (path == NRB_PATH_TC1 && !tc1_eligible(q, b, k)) {
+        set_error("search_flat: NRB_PATH_TC1 needs raw/hi/norms planes on both sides, max_norm on the item "
+                  "side, kp <= 256 and k <= %d", 128 - TC1_EXTRA);
+        return NRB_ERR_INVALID;
+    }
+    if (path != NRB_PATH_TC1) path = resolve_path(path);
+    const FlatPlan p = plan_flat(q->n, b->n, k, path);
+    const FlatWs w = carve_flat(workspace, p, q->n, k, path);
+    if (!workspace || workspace_bytes < w.total) {
+        set_error("search_flat: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return NRB_ERR_WORKSPACE;
+    }
+    int rc;
+    if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.nsplit, p.chunk_rows, st))) return rc;
+    if (path != NRB_PATH_TC1) {
+        {
+            ProfScope prof(st);
+            if (path == NRB_PATH_SIMT)
+                rc = launch_topk_simt_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+            else
+                rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+        }
+        if (rc) return rc;
+        return launch_select(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, metric, nullptr, id_base, D, I, st);
+    }
+    // ---- 1xTF32 filter + exact refine, then the 3xTF32 kernel for whatever was flagged
+    const int pw = k + TC1_EXTRA;
+    const float eps_xmax = TC1_EPS * b->max_norm;
+    NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
+    {
+        ProfScope prof(st);
+        rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
+                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, st);
+    }
+    if (rc) return rc;
+    if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, pw, metric, q, b, eps_xmax,
+                                   id_base, w.flags, D, I, st))) return rc;
+    if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
+    int nflag = 0;
+    NRB_CUDA_CHECK(cudaMemcpyAsync(&nflag, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NRB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (nflag == 0) return NRB_OK;
+    NRB_REQUIRE(q->lo && b->lo, "search_flat: %d queries need the 3xTF32 fallback but the lo planes are missing", nflag);
+    g_fallback_queries += nflag;
+    const size_t plane = (size_t)nflag * q->kp * sizeof(float);
+    const size_t wsb2 = nrb_search_flat_workspace(nflag, b->n, k, q->kp);
+    char* tmp = nullptr;
+    const size_t tmp_bytes = 2 * align_up(plane, 256) + align_up((size_t)nflag * 4, 256) +
+                             align_up((size_t)nflag * k * 4, 256) + align_up((size_t)nflag * k * 8, 256) + wsb2;
+    NRB_CUDA_CHECK(cudaMallocAsync((void**)&tmp, tmp_bytes, st));
+    Carver c(tmp);
+    float* fhi = c.take<float>((size_t)nflag * q->kp);
+    float* flo = c.take<float>((size_t)nflag * q->kp);
+    float* fnr = c.take<float>(nflag);
+    float* Df = c.take<float>((size_t)nflag * k);
+    int64_t* If = c.take<int64_t>((size_t)nflag * k);
+    void* ws2 = c.take<char>(wsb2);
+    rc = launch_gather_rows(q->hi, q->kp, w.flag_list, 1, nflag, fhi, st);
+    if (!rc) rc = launch_gather_rows(q->lo, q->kp, w.flag_list, 1, nflag, flo, st);
+    if (!rc) rc = launch_gather_scalar(q->norms, w.flag_list, 1, nflag, fnr, st);
+    nrb_matrix qf = *q;
+    qf.raw = nullptr;
+    qf.hi = fhi;
+    qf.lo = flo;
+    qf.norms = fnr;
+    qf.n = nflag;
+    if (!rc) rc = search_flat_impl(&qf, b, metric, k, id_base, Df, If, ws2, wsb2, NRB_PATH_TC, st);
+    if (!rc) rc = launch_scatter_results(Df, If, w.flag_list, nflag, k, D, I, st);
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+}  // namespace nrb
 
 extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
                                int64_t id_base, float* D, int64_t* I, void* workspace,
@@ -363,28 +457,14 @@ extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t
     NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "search_flat: k=%d out of range [1,%d]", k, NRB_MAX_K);
     NRB_REQUIRE(q->d == b->d && q->kp == b->kp, "search_flat: dimension mismatch (%d/%d vs %d/%d)", q->d, q->kp, b->d, b->kp);
     NRB_REQUIRE(q->n >= 0 && b->n >= 0 && b->n < (1LL << 31) - 4096 && q->n < (1LL << 31), "search_flat: sizes out of range");
+    NRB_REQUIRE(path >= NRB_PATH_AUTO && path <= NRB_PATH_TC1, "search_flat: bad path %d", path);
     if (q->n == 0) return NRB_OK;
     int rc = require_device();
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    path = resolve_path(path);
-    const FlatPlan p = plan_flat(q->n, b->n, k, path);
-    const FlatWs w = carve_flat(workspace, p, q->n, k, path);
-    if (!workspace || workspace_bytes < w.total) {
-        set_error("search_flat: workspace %zu < %zu bytes", workspace_bytes, w.total);
-        return NRB_ERR_WORKSPACE;
-    }
-    if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.nsplit, p.chunk_rows, st))) return rc;
-    {
-        ProfScope prof(st);
-        if (path == NRB_PATH_SIMT)
-            rc = launch_topk_simt_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
-        else
-            rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
-    }
-    if (rc) return rc;
-    return launch_select(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, metric, nullptr, id_base, D, I, st);
+    return search_flat_impl(q, b, metric, k, id_base, D, I, workspace, workspace_bytes, path, (cudaStream_t)stream);
 }
+
+extern "C" int64_t nrb_fallback_query_count(void) { return (int64_t)g_fallback_queries.load(); }
 
 extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k, int32_t kp,
                                            int32_t nlist, int32_t max_list_len) {

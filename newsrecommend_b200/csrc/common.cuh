@@ -105,12 +105,17 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
     }
 }
 
-// Warp-cooperative prune of one row's candidate buffer: keeps the best `k` of the first `n`
-// entries of (bk, bi), writes them best-first to (ok, oi) (which may alias bk/bi), pads
-// [min(n,k), k) with the empty candidate, and returns the new threshold = key of the k-th best
-// (NEG_INF while fewer than k candidates exist). All 32 lanes must call with identical args.
-__device__ __forceinline__ float warp_prune_row(const float* bk, const int* bi, int n, int k,
-                                                float* ok, int* oi, int lane) {
+// Warp-cooperative prune of one row's candidate buffer. Sorts the first `n` entries of (bk, bi)
+// best-first, finds kth = key of the k-th best (NEG_INF while fewer than k exist) and keeps the
+// best k PLUS every entry whose key is within `margin` of kth (key > kth - margin), at most
+// `keep_max`; writes `width` entries to (ok, oi) (kept ones, then empty candidates; ok/oi may
+// alias bk/bi). Returns the new append threshold kth - margin; *kept = entries kept; *overflow
+// is set when more than keep_max entries were within the margin (the row is then incomplete
+// and must be recomputed by the exact path). margin = 0, keep_max = width = k is the plain
+// top-k prune. All 32 lanes must call with identical arguments.
+__device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi, int n, int k, float margin,
+                                                  int keep_max, int width, float* ok, int* oi, int lane,
+                                                  int* kept, bool* overflow) {
     constexpr int R = CAND_CAP / 32;
     uint64_t c[R];
 #pragma unroll
@@ -123,17 +128,42 @@ __device__ __forceinline__ float warp_prune_row(const float* bk, const int* bi, 
     float kth = NEG_INF;
     const int kl = (k - 1) & 31, ki = (k - 1) >> 5;
 #pragma unroll
+    for (int i = 0; i < R; i++)
+        if (i == ki) kth = cand_key(c[i]);
+    kth = __shfl_sync(0xffffffffu, kth, kl);
+    const float thr = kth - margin;  // NEG_INF stays NEG_INF
+    int cnt = 0;
+#pragma unroll
     for (int i = 0; i < R; i++) {
         const int e = i * 32 + lane;
-        if (e < k) {
-            ok[e] = cand_key(c[i]);
-            oi[e] = cand_idx(c[i]);
-        }
-        if (i == ki) kth = cand_key(c[i]);
+        cnt += (e < n && cand_key(c[i]) > thr) ? 1 : 0;
     }
-    kth = __shfl_sync(0xffffffffu, kth, kl);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int base = n < k ? n : k;
+    cnt = cnt > base ? cnt : base;
+    *overflow = cnt > keep_max;
+    cnt = cnt > keep_max ? keep_max : cnt;
+    *kept = cnt;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const int e = i * 32 + lane;
+        if (e < width) {
+            const bool keep = e < cnt;
+            ok[e] = keep ? cand_key(c[i]) : NEG_INF;
+            oi[e] = keep ? cand_idx(c[i]) : -1;
+        }
+    }
     __syncwarp();
-    return kth;  // NEG_INF if the k-th slot is an empty candidate
+    return thr;
+}
+
+// Plain top-k prune (margin 0): keeps min(n, k) entries, returns kth.
+__device__ __forceinline__ float warp_prune_row(const float* bk, const int* bi, int n, int k,
+                                                float* ok, int* oi, int lane) {
+    int kept;
+    bool ovf;
+    return warp_prune_row_m(bk, bi, n, k, 0.f, k, k, ok, oi, lane, &kept, &ovf);
 }
 
 }  // namespace nrb

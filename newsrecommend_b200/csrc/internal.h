@@ -30,6 +30,17 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
                        const int* n_units_dev, int grid, int metric, int k, float* part_key,
                        int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+// 1xTF32 filter + exact refine (NRB_PATH_TC1): partial rows are `pw` = k + TC1_EXTRA wide and hold
+// every candidate within the error margin of the k-th; row_flags[a_row] = 1 marks rows whose
+// margin set did not fit. margin_scale = 2 * eps * max|x| (the kernel multiplies by |q|).
+constexpr int TC1_EXTRA = 32;
+constexpr float TC1_EPS = 1.1f / 1024.f;  // both operands rounded to tf32 (2 * 2^-11) + accumulation slack
+int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
+int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
+                        const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
+                        float* part_key, int* part_idx, int* row_flags, void* scratch,
+                        size_t scratch_bytes, cudaStream_t st);
+
 // ---- topk_simt.cu: fp32 CUDA-core distance + selection over the same Unit list
 size_t simt_scratch_bytes(int grid);
 int simt_grid(int n_units_upper);
@@ -43,6 +54,12 @@ int launch_topk_simt_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* u
 int launch_select(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
                   int k, int metric, const int64_t* id_map, int64_t id_base, float* D, int64_t* I,
                   cudaStream_t st);
+int launch_select_refine(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
+                         int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
+                         int64_t id_base, int* flags, float* D, int64_t* I, cudaStream_t st);
+int launch_compact_flags(const int* flags, int64_t n, int* list, int* count, cudaStream_t st);
+int launch_scatter_results(const float* Df, const int64_t* If, const int* list, int n, int k, float* D,
+                           int64_t* I, cudaStream_t st);
 int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
                            int nsplit, int chunk_rows, cudaStream_t st);
 size_t counting_sort_ws(int64_t n, int nb);

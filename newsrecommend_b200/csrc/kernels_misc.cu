@@ -366,6 +366,118 @@ __global__ void shard_merge_kernel(ShardSource S, float* __restrict__ D, int64_t
     }
 }
 
+// Merge + exact refine of the 1xTF32 filter (NRB_PATH_TC1). One warp per query: k-way merge of
+// the partial rows (approximate keys), cut at (k-th approximate key - margin), exact fp32
+// rescoring of the surviving candidates from the raw planes (coalesced float4 row reads, warp
+// reduction), sort by the exact key, write the best k. flags[q] is raised when the candidate
+// slots were exhausted inside the margin or when an exact score disagrees with its estimate by
+// more than the assumed error bound; flagged queries are recomputed by the 3xTF32 kernel.
+template <int MAXL, bool L2>
+__global__ void select_refine_kernel(PartSource S, int64_t nq, int k, const float* __restrict__ q_raw,
+                                     const float* __restrict__ q_norms, const float* __restrict__ b_raw,
+                                     const float* __restrict__ b_norms, int kp, float eps_xmax,
+                                     int64_t id_base, int* __restrict__ flags, float* __restrict__ D,
+                                     int64_t* __restrict__ I) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int pw = S.k;
+    uint64_t res[4];
+    warp_kway_merge<MAXL>(S, q, pw, lane, res);
+    const float qn = q_norms[q];
+    const float ebound = eps_xmax * sqrtf(qn) * (L2 ? 2.f : 1.f);
+    const float margin = 2.f * ebound;
+    float ak = NEG_INF;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i == ((k - 1) >> 5)) ak = cand_key(res[i]);
+    ak = __shfl_sync(0xffffffffu, ak, (k - 1) & 31);
+    const float cut = ak - margin;
+    int nv = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = i * 32 + lane;
+        nv += (r < pw && cand_idx(res[i]) >= 0 && (r < k || cand_key(res[i]) > cut)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    bool bad = (nv >= pw);  // every slot is inside the margin: more candidates may exist
+    // query row in registers
+    const int w4 = kp >> 2;
+    float4 qv[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int c = lane + 32 * j;
+        qv[j] = c < w4 ? __ldg(reinterpret_cast<const float4*>(q_raw + q * kp) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint64_t ex[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) ex[i] = empty_cand();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        for (int l = 0; l < 32; l++) {
+            const int r = i * 32 + l;
+            if (r >= nv) break;  // warp-uniform
+            const int idx = __shfl_sync(0xffffffffu, cand_idx(res[i]), l);
+            const float approx = __shfl_sync(0xffffffffu, cand_key(res[i]), l);
+            const float4* xr = reinterpret_cast<const float4*>(b_raw + (int64_t)idx * kp);
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int c = lane + 32 * j;
+                if (c < w4) {
+                    const float4 xv = __ldg(xr + c);
+                    acc = fmaf(qv[j].x, xv.x, acc);
+                    acc = fmaf(qv[j].y, xv.y, acc);
+                    acc = fmaf(qv[j].z, xv.z, acc);
+                    acc = fmaf(qv[j].w, xv.w, acc);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            float key = acc;
+            if (L2) key = -fmaxf(qn + b_norms[idx] - 2.f * acc, 0.f);
+            if (fabsf(key - approx) > ebound) bad = true;
+            if (lane == l) ex[i] = pack_cand(key, idx);
+        }
+    }
+    warp_bitonic_desc<4>(ex, lane);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = i * 32 + lane;
+        if (r < k) {
+            const int idx = cand_idx(ex[i]);
+            const float key = cand_key(ex[i]);
+            if (idx < 0) {
+                I[q * k + r] = -1;
+                D[q * k + r] = L2 ? FLT_MAX : -FLT_MAX;
+            } else {
+                I[q * k + r] = (int64_t)idx + id_base;
+                D[q * k + r] = L2 ? -key : key;
+            }
+        }
+    }
+    if (bad && lane == 0) flags[q] = 1;
+}
+
+__global__ void compact_flags_kernel(const int* __restrict__ flags, int64_t n, int* __restrict__ list,
+                                     int* __restrict__ count) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (flags[i]) list[atomicAdd(count, 1)] = (int)i;
+}
+
+__global__ void scatter_results_kernel(const float* __restrict__ Df, const int64_t* __restrict__ If,
+                                       const int* __restrict__ list, int n, int k, float* __restrict__ D,
+                                       int64_t* __restrict__ I) {
+    const int64_t total = (int64_t)n * k;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / k), j = (int)(t - (int64_t)i * k);
+        const int64_t o = (int64_t)list[i] * k + j;
+        D[o] = Df[t];
+        I[o] = If[t];
+    }
+}
+
 // Units + src table of the flat search: unit u = s*nqt2 + t covers query tile t and item chunk
 // s (nqt2 = nqt rounded up to even; the odd tile out is a phantom unit with a_rows = 0, so that
 // units 2p and 2p+1 always share their item rows -- the CTA-pair kernel needs that).
@@ -413,6 +525,58 @@ int launch_select(const float* part_key, const int* part_idx, const int* src, in
         select_merge_kernel<4><<<blocks, wpb * 32, 0, st>>>(ps, nq, metric, id_map, id_base, D, I);
     else
         select_merge_kernel<8><<<blocks, wpb * 32, 0, st>>>(ps, nq, metric, id_map, id_base, D, I);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_select_refine(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
+                         int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
+                         int64_t id_base, int* flags, float* D, int64_t* I, cudaStream_t st) {
+    if (nq == 0) return NRB_OK;
+    NRB_REQUIRE(S >= 1 && S <= 256 && pw <= 128 && k <= pw && q->kp <= 256, "select_refine: S=%d pw=%d kp=%d", S, pw, q->kp);
+    PartSource ps{part_key, part_idx, src, S, pw};
+    const int wpb = 8;
+    const unsigned blocks = (unsigned)((nq + wpb - 1) / wpb);
+#define NRB_SR(MAXL)                                                                                         \
+    do {                                                                                                     \
+        if (metric == NRB_METRIC_L2)                                                                         \
+            select_refine_kernel<MAXL, true><<<blocks, wpb * 32, 0, st>>>(ps, nq, k, q->raw, q->norms, b->raw, \
+                                                                          b->norms, q->kp, eps_xmax, id_base, \
+                                                                          flags, D, I);                      \
+        else                                                                                                 \
+            select_refine_kernel<MAXL, false><<<blocks, wpb * 32, 0, st>>>(ps, nq, k, q->raw, q->norms, b->raw, \
+                                                                           b->norms, q->kp, eps_xmax, id_base, \
+                                                                           flags, D, I);                     \
+    } while (0)
+    if (S <= 32)
+        NRB_SR(1);
+    else if (S <= 64)
+        NRB_SR(2);
+    else if (S <= 128)
+        NRB_SR(4);
+    else
+        NRB_SR(8);
+#undef NRB_SR
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_compact_flags(const int* flags, int64_t n, int* list, int* count, cudaStream_t st) {
+    NRB_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    compact_flags_kernel<<<(unsigned)blocks, 256, 0, st>>>(flags, n, list, count);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_scatter_results(const float* Df, const int64_t* If, const int* list, int n, int k, float* D,
+                           int64_t* I, cudaStream_t st) {
+    if (n == 0) return NRB_OK;
+    int64_t blocks = ((int64_t)n * k + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    scatter_results_kernel<<<(unsigned)blocks, 256, 0, st>>>(Df, If, list, n, k, D, I);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

@@ -67,8 +67,10 @@ constexpr size_t V2_SMEM = (size_t)V2_STAGES * V2_STAGE_BYTES + sizeof(TcShared<
 // ---------------------------------------------------------------------------- epilogue
 struct EpiRow {
     int cnt;
-    float thr;
-    float qn;
+    float thr;     // append threshold: kth - margin (NEG_INF until k candidates exist)
+    float qn;      // squared query norm (L2 keys, margins)
+    float margin;  // 0 for the 3xTF32 kernels; error margin of the 1xTF32 filter
+    int flag;      // set when more than keep_max candidates fell inside the margin
 };
 
 // One 128 x 256 accumulator: thread = query row, 8 chunks of 32 columns.
@@ -79,7 +81,8 @@ struct EpiRow {
 //   ck/ci   candidate buffers of this warp's 32 rows; myk/myi = this lane's row
 template <bool L2>
 __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
-                                         float* ck, int* ci, float* myk, int* myi, int k, int lane) {
+                                         float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
+                                         int lane) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         if (c0 >= valid) break;  // warp-uniform
@@ -111,25 +114,34 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const int n = __shfl_sync(0xffffffffu, st.cnt, src);
+            const float mg = __shfl_sync(0xffffffffu, st.margin, src);
             float* rk = ck + (int64_t)src * CAND_CAP;
             int* ri = ci + (int64_t)src * CAND_CAP;
-            const float tnew = warp_prune_row(rk, ri, n, k, rk, ri, lane);
+            int kept;
+            bool ovf;
+            const float tnew = warp_prune_row_m(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, lane, &kept, &ovf);
             if (lane == src) {
-                st.cnt = n < k ? n : k;
+                st.cnt = kept;
                 st.thr = tnew;
+                st.flag |= ovf ? 1 : 0;
             }
         }
     }
 }
 
-// Unit finished: best-first top-k of the warp's 32 rows into the unit's partial rows.
-__device__ __forceinline__ void epi_unit_end(const EpiRow& st, float* ck, int* ci, int u, int quad, int k,
+// Unit finished: the warp's 32 rows, best-first, into the unit's partial rows (`pw` entries
+// per row: the best k plus, for the margin filter, everything within the margin of the k-th).
+__device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int u, int quad, int k, int pw,
                                              float* part_key, int* part_idx, int lane) {
     for (int src = 0; src < 32; src++) {
         const int n = __shfl_sync(0xffffffffu, st.cnt, src);
-        const int64_t o = ((int64_t)u * UNIT_ROWS + quad * 32 + src) * k;
-        warp_prune_row(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, part_key + o,
-                       part_idx + o, lane);
+        const float mg = __shfl_sync(0xffffffffu, st.margin, src);
+        const int64_t o = ((int64_t)u * UNIT_ROWS + quad * 32 + src) * pw;
+        int kept;
+        bool ovf;
+        warp_prune_row_m(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, mg, pw, pw,
+                         part_key + o, part_idx + o, lane, &kept, &ovf);
+        if (lane == src) st.flag |= ovf ? 1 : 0;
     }
 }
 
@@ -276,6 +288,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             st.cnt = 0;
             st.thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
             st.qn = 0.f;
+            st.margin = 0.f;
+            st.flag = 0;
             if (L2) {
                 const int64_t ar = (int64_t)un.a_row0 + row;
                 st.qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
@@ -287,14 +301,14 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 ptx::mbar_wait(&sh->tfull[acc], acc_phase);
                 ptx::tcgen05_fence_after();
                 const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, lane);
+                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, k, lane);
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&sh->tempty[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            epi_unit_end(st, ck, ci, u, quad, k, part_key, part_idx, lane);
+            epi_unit_end(st, ck, ci, u, quad, k, k, part_key, part_idx, lane);
         }
     }
 
@@ -445,6 +459,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             st.cnt = 0;
             st.thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
             st.qn = 0.f;
+            st.margin = 0.f;
+            st.flag = 0;
             if (L2) {
                 const int64_t ar = (int64_t)un.a_row0 + row;
                 st.qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
@@ -456,20 +472,216 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 ptx::mbar_wait(&sh->tfull[acc], acc_phase);
                 ptx::tcgen05_fence_after();
                 const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, lane);
+                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, k, lane);
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_cluster(tempty0[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
-            epi_unit_end(st, ck, ci, u, quad, k, part_key, part_idx, lane);
+            epi_unit_end(st, ck, ci, u, quad, k, k, part_key, part_idx, lane);
         }
     }
 
     ptx::tcgen05_fence_before();
     __syncwarp();
     ptx::cluster_sync_all();  // both CTAs are done with the pair's TMEM and barriers
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    }
+}
+
+
+// ---------------------------------------------------------------------------- v3: 1xTF32 filter
+// CTA pairs again, but ONE tf32 pass (hi planes only) and the query tile resident in shared
+// memory for the whole unit (128 rows x kp <= 256 fp32 = 128 KB), so only the item half-tiles
+// stream (16 KB stages, 5 deep). The scores carry a bounded error |a - s| <= eps*|q|*|x| with
+// eps ~ 2^-10 (both operands rounded to tf32), so the epilogue keeps, per row, the best k AND
+// every candidate within margin = 2*eps*|q|*max|x| of the k-th: that set provably contains the
+// true top-k. select_refine_kernel rescoring those <= k+32 candidates exactly in fp32 gives
+// the final order; rows with more candidates than slots are flagged and recomputed by the
+// 3xTF32 kernel.
+constexpr int V3_STAGES = 5;
+constexpr int V3_MAX_NKC = 8;
+constexpr int V3_A_BYTES = V3_MAX_NKC * A_BYTES;  // 128 KB resident query tile
+
+struct Tc3Shared {
+    uint64_t full[V3_STAGES];
+    uint64_t empty[V3_STAGES];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint64_t afull;
+    uint64_t aempty;
+    uint32_t tmem_base;
+    uint32_t pad;
+    float nrm[2][BN];
+};
+constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared) + 1024;
+
+template <bool L2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_bh,
+                const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc, int k, int pw,
+                float margin_scale, const float* __restrict__ a_norms, const float* __restrict__ b_norms,
+                int64_t a_total, int64_t b_total, float* __restrict__ part_key, int* __restrict__ part_idx,
+                int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf) {
+    constexpr int STAGES = V3_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem + V3_A_BYTES;
+    Tc3Shared* sh = reinterpret_cast<Tc3Shared*>(smem_b + (size_t)STAGES * BH_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = (*n_units_p + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&sh->full[s], 1);
+            ptx::mbar_init(&sh->empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&sh->tfull[a], 1);
+            ptx::mbar_init(&sh->tempty[a], 8);
+        }
+        ptx::mbar_init(&sh->afull, 1);
+        ptx::mbar_init(&sh->aempty, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&map_ah);
+        ptx::prefetch_tensormap(&map_bh);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_cg2(&sh->tmem_base, TMEM_COLS);
+        ptx::tmem_relinquish_cg2();
+    }
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    ptx::cluster_sync_all();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            uint32_t full0[STAGES];
+            for (int s = 0; s < STAGES; s++) full0[s] = ptx::mapa_u32(&sh->full[s], 0);
+            const uint32_t afull0 = ptx::mapa_u32(&sh->afull, 0);
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+                const Unit un = units[2 * p + rank];
+                const int ntiles = (un.b_rows + BN - 1) / BN;
+                // the unit's query tile, once
+                ptx::mbar_wait(&sh->aempty, a_phase ^ 1);
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
+                for (int kc = 0; kc < nkc; kc++)
+                    ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KC, un.a_row0);
+                a_phase ^= 1;
+                for (int t = 0; t < ntiles; t++) {
+                    const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);
+                    for (int kc = 0; kc < nkc; kc++) {
+                        ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * BH_BYTES);
+                        ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BH_BYTES, &map_bh, full0[stage], kc * KC, brow);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * BM, BN);
+            const uint32_t sa0 = ptx::smem_u32(smem);
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+                const Unit un = units[2 * p];
+                const int ntiles = (un.b_rows + BN - 1) / BN;
+                ptx::mbar_wait(&sh->afull, a_phase);
+                ptx::tcgen05_fence_after();
+                a_phase ^= 1;
+                for (int t = 0; t < ntiles; t++) {
+                    ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kc = 0; kc < nkc; kc++) {
+                        ptx::mbar_wait(&sh->full[stage], phase);
+                        ptx::tcgen05_fence_after();
+                        const uint32_t s_a = sa0 + (uint32_t)kc * A_BYTES;
+                        const uint32_t s_b = ptx::smem_u32(smem_b + (size_t)stage * BH_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ks++) {
+                            const uint32_t off = ks * 32;
+                            ptx::umma_tf32_cg2(d_tmem, ptx::umma_desc_sw128(s_a + off), ptx::umma_desc_sw128(s_b + off),
+                                               idesc, (kc | ks) != 0);
+                        }
+                        ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+                ptx::umma_commit_cg2_mc(&sh->aempty, 3);  // query tile may be replaced once these MMAs retire
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ filter epilogue (both CTAs)
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int etid = (warp - 2) * 32 + lane;
+        float* ck = cand_key_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
+        int* ci = cand_idx_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
+        float* myk = ck + (int64_t)lane * CAND_CAP;
+        int* myi = ci + (int64_t)lane * CAND_CAP;
+        const uint32_t tempty0[2] = {ptx::mapa_u32(&sh->tempty[0], 0), ptx::mapa_u32(&sh->tempty[1], 0)};
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+            const int u = 2 * p + (int)rank;
+            const Unit un = units[u];
+            const int ntiles = (un.b_rows + BN - 1) / BN;
+            const int64_t ar = (int64_t)un.a_row0 + row;
+            const bool live = row < un.a_rows && ar < a_total;
+            EpiRow st;
+            st.cnt = 0;
+            st.thr = live ? NEG_INF : __builtin_huge_valf();
+            st.qn = live ? a_norms[ar] : 0.f;
+            st.margin = margin_scale * sqrtf(st.qn) * (L2 ? 2.f : 1.f);
+            st.flag = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int col_base = t * BN;
+                const int valid = un.b_rows - col_base;
+                epi_stage_norms<L2>(sh->nrm[acc], b_norms, un, col_base, valid, b_total, etid);
+                ptx::mbar_wait(&sh->tfull[acc], acc_phase);
+                ptx::tcgen05_fence_after();
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, pw, lane);
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(tempty0[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            epi_unit_end(st, ck, ci, u, quad, k, pw, part_key, part_idx, lane);
+            if (st.flag && live) row_flags[ar] = 1;
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    ptx::cluster_sync_all();
     if (warp == 1) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
@@ -593,6 +805,44 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
             NRB_TC_LAUNCH(topk_tc2_kernel<false>, V2_SMEM);
     }
 #undef NRB_TC_LAUNCH
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
+    return a->hi && b->hi && a->raw && b->raw && a->norms && b->norms && b->max_norm > 0.f &&
+           a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && k + TC1_EXTRA <= 128;
+}
+
+int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
+                        const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
+                        float* part_key, int* part_idx, int* row_flags, void* scratch,
+                        size_t scratch_bytes, cudaStream_t st) {
+    NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", 128 - TC1_EXTRA);
+    NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - 64, "tc1: bad kp / pw");
+    NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
+    if (scratch_bytes < tc_scratch_bytes(grid)) {
+        set_error("tc1: scratch too small");
+        return NRB_ERR_WORKSPACE;
+    }
+    CUtensorMap mah, mbh;
+    int rc;
+    if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
+    if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN / 2))) return rc;
+    float* ck = (float*)scratch;
+    int* ci = (int*)((char*)scratch + (size_t)grid * BM * CAND_CAP * sizeof(float));
+    const int nkc = a->kp / KC;
+    if (metric == NRB_METRIC_L2) {
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
+        topk_tc3_kernel<true><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
+                                                                  a->norms, b->norms, a->n, b->n, part_key, part_idx,
+                                                                  row_flags, ck, ci);
+    } else {
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
+        topk_tc3_kernel<false><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
+                                                                   a->norms, b->norms, a->n, b->n, part_key, part_idx,
+                                                                   row_flags, ck, ci);
+    }
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

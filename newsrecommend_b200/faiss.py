@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import METRIC_INNER_PRODUCT, METRIC_L2, PATH_AUTO, PATH_SIMT, PATH_TC, Matrix, check, lib
+from ._lib import METRIC_INNER_PRODUCT, METRIC_L2, PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1, Matrix, check, lib
 
 __all__ = [
     "METRIC_INNER_PRODUCT", "METRIC_L2", "IndexFlat", "IndexFlatL2", "IndexFlatIP", "IndexHNSWFlat",
@@ -78,7 +78,7 @@ class PackedMatrix:
     """Device form of a row-major fp32 matrix: zero-padded raw rows, tf32 hi / lo planes and
     squared norms (struct nrb_matrix). Grows geometrically on append."""
 
-    def __init__(self, d: int, device=None, planes=("raw", "hi", "lo", "norms")):
+    def __init__(self, d: int, device=None, planes=("raw", "hi", "lo", "norms"), track_max_norm=False):
         self.d = d
         self.kp = _round_kp(d)
         self.n = 0
@@ -86,6 +86,10 @@ class PackedMatrix:
         self.planes = planes
         self._cap = 0
         self.raw = self.hi = self.lo = self.norms = None
+        # max row norm: the item side of the 1xTF32 filter (NRB_PATH_TC1) needs it; costs one
+        # small reduction + sync per append, so only index storage tracks it
+        self.track_max_norm = track_max_norm and "norms" in planes
+        self.max_norm = 0.0
 
     def _reserve(self, n: int):
         if n <= self._cap:
@@ -113,10 +117,13 @@ class PackedMatrix:
                 _ptr(self.hi[off:]) if self.hi is not None else 0,
                 _ptr(self.lo[off:]) if self.lo is not None else 0,
                 _ptr(self.norms[off:]) if self.norms is not None else 0, _stream()), "pack_rows")
+            if self.track_max_norm:
+                self.max_norm = max(self.max_norm, float(self.norms[off:off + m].max().sqrt()))
         self.n += m
 
     def clear(self):
         self.n = 0
+        self.max_norm = 0.0
 
     def struct(self, row0: int = 0, rows: int | None = None) -> Matrix:
         rows = self.n - row0 if rows is None else rows
@@ -126,6 +133,7 @@ class PackedMatrix:
         m.lo = _ptr(self.lo[row0:]) if self.lo is not None else None
         m.norms = _ptr(self.norms[row0:]) if self.norms is not None else None
         m.n, m.d, m.kp = rows, self.d, self.kp
+        m.max_norm = self.max_norm if self.track_max_norm else 0.0
         return m
 
     @classmethod
@@ -160,7 +168,9 @@ class IndexFlat:
         self.metric_type = metric
         self.is_trained = True
         self.verbose = False
-        self.path = PATH_AUTO  # PATH_SIMT forces the fp32 CUDA-core kernels
+        # PATH_AUTO: 1xTF32 filter + exact refine (PATH_TC1) when eligible, else 3xTF32 (PATH_TC);
+        # PATH_TC forces 3xTF32, PATH_SIMT the fp32 CUDA-core kernels
+        self.path = PATH_AUTO
         self._xb: PackedMatrix | None = None
 
     @property
@@ -174,7 +184,7 @@ class IndexFlat:
         t, _ = _to_device_f32(x)
         assert t.shape[1] == self.d
         if self._xb is None:
-            self._xb = PackedMatrix(self.d, t.device)
+            self._xb = PackedMatrix(self.d, t.device, track_max_norm=True)
         self._xb.append(t)
 
     def reset(self):
@@ -183,7 +193,7 @@ class IndexFlat:
 
     def _packed(self) -> PackedMatrix:
         if self._xb is None:
-            self._xb = PackedMatrix(self.d)
+            self._xb = PackedMatrix(self.d, track_max_norm=True)
         return self._xb
 
     def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0):
@@ -202,6 +212,8 @@ class IndexFlat:
         return D, I
 
     def _query_planes(self):
+        if self.path in (PATH_AUTO, PATH_TC1):
+            return ("raw", "hi", "lo", "norms")  # lo only feeds the (rare) 3xTF32 fallback
         need = ("raw",) if self.path == PATH_SIMT else ("hi", "lo")
         return need + (("norms",) if self.metric_type == METRIC_L2 else ())
 

@@ -34,6 +34,11 @@ for nlist in NLISTS:
     (D, I), t_search = timed(lambda: ivf.search(xq_d, 50))
     kms, kn = _lib.profile_read(); _lib.profile_enable(False)
     rec = recall_at_k(I[:20000].cpu().numpy(), I_exact.cpu().numpy())
+    # rows actually scanned: sum over (query, probed list) of the list length
+    qp = nf.PackedMatrix.from_tensor(xq_d, planes=("hi", "lo"))
+    _, coarse = quant.search_packed(qp, 16)
+    scanned = int(torch.from_numpy(sizes).cuda()[coarse.reshape(-1)].sum().item())
+    del qp
     # teacher-forced parity sample: oracle IVF with the same centroids and list contents
     cent = quant.reconstruct_n()
     qo = fo.IndexFlatIP(250); qo.add(cent)
@@ -44,6 +49,8 @@ for nlist in NLISTS:
     same_lists = bool(np.array_equal(sizes, ivf_o.list_sizes()))
     print(json.dumps(dict(nlist=nlist, nq=NQ, nprobe=16, k=50, train_s=t_train, niter=ivf.cp.niter, add_s=t_add,
                           search_s=t_search, search_qps=NQ / t_search, scan_kernel_ms=kms, scan_kernel_launches=kn,
+                          scanned_rows=scanned, scan_alg_tflop=2.0 * scanned * 250 / 1e12,
+                          scanned_frac_of_flat=scanned / (NQ * float(synth.N_ARTICLES)),
                           list_min=int(sizes.min()), list_max=int(sizes.max()),
                           imbalance=float((sizes.astype(np.float64) ** 2).sum() * nlist / sizes.sum() ** 2),
                           recall_vs_exact=rec, oracle_same_lists=same_lists,

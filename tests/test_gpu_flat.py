@@ -10,7 +10,7 @@ from newsrecommend_b200.parity import compare_topk
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-PATHS = {"tc": 2, "simt": 1}
+PATHS = {"tc": 2, "simt": 1, "tc1": 3, "auto": 0}
 
 
 def _l2_scale(xq, xb):
@@ -42,7 +42,7 @@ def test_pack_rows_split_is_exact(nf):
     assert np.allclose(p.norms[:1000].cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=1e-5)
 
 
-@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "auto"])
 @pytest.mark.parametrize("metric", [0, 1])
 def test_golden_fixture(nf, path, metric):
     g = np.load(os.path.join(GOLDEN, "flat_small.npz"))
@@ -52,7 +52,7 @@ def test_golden_fixture(nf, path, metric):
     assert rep["ok"], rep
 
 
-@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "auto"])
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("nq,nb,d,k", [
     (1, 5000, 250, 50), (19, 5000, 250, 50), (20, 5000, 256, 50), (129, 3001, 250, 20),
@@ -60,6 +60,8 @@ def test_golden_fixture(nf, path, metric):
     (130, 7, 12, 10), (5, 1, 40, 3), (1000, 20000, 250, 128),
 ])
 def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
+    if path == "tc1" and (k > 96 or d > 256):
+        pytest.skip("NRB_PATH_TC1 covers k <= 96 and d <= 256 (PATH_AUTO routes the rest to 3xTF32)")
     rng = np.random.default_rng(nq * 1000 + nb + d + k)
     xb = rng.standard_normal((nb, d), dtype=np.float32)
     xq = rng.standard_normal((nq, d), dtype=np.float32)
@@ -70,7 +72,7 @@ def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
     assert rep["recall"] == 1.0 or rep["tie_exempt_queries"] > 0
 
 
-@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc1"])
 def test_identity_duplicates_and_padding(nf, path):
     d = 32
     eye = np.eye(d, dtype=np.float32)
@@ -195,3 +197,32 @@ def test_tc_kernel_variants(nf, oracle, variant, metric):
             assert rep["ok"], (variant, nq, nb, d, k, rep)
     finally:
         lib.nrb_set_tc_variant(2)
+
+
+def test_tc1_filter_margin_and_fallback(nf, oracle):
+    """The 1xTF32 filter: (a) on ordinary data no query needs the 3xTF32 fallback, i.e. every
+    estimate stayed inside the assumed error bound and the margin set fitted its slots;
+    (b) with hundreds of exact duplicates the margin set overflows, the queries are flagged,
+    recomputed by the 3xTF32 kernel, and the result is still a valid top-k."""
+    from newsrecommend_b200 import synth
+    from newsrecommend_b200._lib import lib
+    xb, topics = synth.g_skew(50000, 250, 3, return_topics=True)
+    xq = synth.user_profiles(xb, topics, 2000, 4)
+    for metric in (0, 1):
+        n0 = lib.nrb_fallback_query_count()
+        D, I = _search(nf, xb, xq, 50, metric, "tc1")
+        assert lib.nrb_fallback_query_count() == n0, "fallback used on ordinary data"
+        Do, Io = oracle.knn_fast(xq, xb, 50, metric)
+        rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
+        assert rep["ok"], rep
+    rng = np.random.default_rng(8)
+    base = rng.standard_normal((20, 64), dtype=np.float32)
+    xb = np.concatenate([np.repeat(base, 150, axis=0), rng.standard_normal((2000, 64), dtype=np.float32)])
+    xq = base + 0.01 * rng.standard_normal((20, 64), dtype=np.float32)
+    n0 = lib.nrb_fallback_query_count()
+    D, I = _search(nf, xb, xq, 10, 0, "tc1")
+    assert lib.nrb_fallback_query_count() >= n0 + 20
+    for q in range(20):
+        assert len(set(I[q].tolist())) == 10 and (I[q] // 150 == q).all()  # ten of the 150 copies of base[q]
+    Do, Io = oracle.knn_fast(xq, xb, 10, 0)
+    assert np.allclose(D, Do, rtol=1e-4)
