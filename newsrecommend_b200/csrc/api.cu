@@ -65,38 +65,62 @@ struct Carver {
 };
 
 // ------------------------------------------------------------------------------ flat plan
+// Query tiles (128 rows) are taken in PAIRS (the CTA-pair kernels need units 2p, 2p+1 to share
+// their item rows). With P pairs and C concurrently resident CTA pairs:
+//   * the first R = floor(P / C) * C pairs are FULL units: one pass over the whole catalog, so
+//     the running top-k threshold warms up once (appends and prunes grow with log(items), a
+//     catalog split s ways pays the warm-up s times);
+//   * the remaining T = P - R pairs are TAIL units, split s ways over the item rows (s chosen
+//     so that T*s fills whole waves), ordered chunk-major so that concurrent CTAs stream the
+//     same item rows.
+// Every query therefore has S = max(1, s) source slots per epilogue warpgroup.
 struct FlatPlan {
-    int nqt, nsplit, chunk_rows, n_units, grid;
+    int nqt;         // query tiles
+    int npairs;      // ceil(nqt / 2)
+    int full_pairs;  // R
+    int tail_pairs;  // T
+    int tsplit;      // s (>= 1)
+    int chunk_rows;  // item rows per tail chunk (multiple of 256)
+    int n_units;     // 2 * (R + T * s)
+    int wgs;         // epilogue warpgroups writing partial rows (2 for the tcgen05 kernels)
+    int S;           // source slots per query = tsplit * wgs
+    int grid;
 };
 
 static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
+    (void)k;
     FlatPlan p;
-    const int sms = sm_count() * (path == NRB_PATH_SIMT ? 2 : 1);
+    const bool simt = path == NRB_PATH_SIMT;
+    p.wgs = simt ? 1 : 2;
     p.nqt = (int)((nq + UNIT_ROWS - 1) / UNIT_ROWS);
     if (p.nqt < 1) p.nqt = 1;
+    p.npairs = (p.nqt + 1) / 2;
+    const int C = simt ? sm_count() : sm_count() / 2;  // units in flight: SIMT runs 2 CTAs per SM
     const int tile = 256;
     int nbt = (int)((nb + tile - 1) / tile);
     if (nbt < 1) nbt = 1;
-    int max_split = 64;  // sources per query in the k-way merge
-    if (max_split > nbt) max_split = nbt;
-    if (max_split < 1) max_split = 1;
+    p.full_pairs = (p.npairs / C) * C;
+    p.tail_pairs = p.npairs - p.full_pairs;
     int best = 1;
-    double best_eff = 0;
-    const int nqt2 = (p.nqt + 1) & ~1;
-    for (int s = 1; s <= max_split; s++) {
-        const double units = (double)p.nqt * s;
-        const double waves = (double)(((int64_t)nqt2 * s + sms - 1) / sms);
-        const double eff = units / (waves * sms);
-        if (eff > best_eff + 0.02) {
-            best_eff = eff;
-            best = s;
+    if (p.tail_pairs > 0) {
+        int max_split = nbt < 64 ? nbt : 64;
+        const double ideal = (double)p.tail_pairs / C;
+        double best_cost = 1e30;
+        for (int s = 1; s <= max_split; s++) {
+            const double cost = (double)(((int64_t)p.tail_pairs * s + C - 1) / C) / s;  // catalogs per CTA pair
+            if (cost < best_cost * 0.97) {  // prefer fewer splits unless >3% better
+                best_cost = cost;
+                best = s;
+            }
+            if (cost <= ideal * 1.02) break;
         }
     }
     const int tiles_per = (nbt + best - 1) / best;
     p.chunk_rows = tiles_per * tile;
-    p.nsplit = (nbt + tiles_per - 1) / tiles_per;
-    p.n_units = ((p.nqt + 1) & ~1) * p.nsplit;  // query tiles padded to whole CTA pairs
-    p.grid = path == NRB_PATH_SIMT ? simt_grid(p.n_units) : tc_grid(p.n_units);
+    p.tsplit = (nbt + tiles_per - 1) / tiles_per;
+    p.n_units = 2 * (p.full_pairs + p.tail_pairs * p.tsplit);
+    p.S = p.tsplit * p.wgs;
+    p.grid = simt ? simt_grid(p.n_units) : tc_grid(p.n_units);
     return p;
 }
 
@@ -118,9 +142,9 @@ static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int pat
     const int pw = path == NRB_PATH_TC1 ? k + TC1_EXTRA : k;  // partial row width
     w.units = c.take<Unit>(p.n_units);
     w.n_units = c.take<int>(1);
-    w.src = c.take<int>((size_t)nq * p.nsplit);
-    w.part_key = c.take<float>((size_t)p.n_units * UNIT_ROWS * pw);
-    w.part_idx = c.take<int>((size_t)p.n_units * UNIT_ROWS * pw);
+    w.src = c.take<int>((size_t)nq * p.S);
+    w.part_key = c.take<float>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
+    w.part_idx = c.take<int>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
     w.flags = w.flag_list = w.flag_count = nullptr;
     if (path == NRB_PATH_TC1) {
         w.flags = c.take<int>(nq);
@@ -213,23 +237,25 @@ __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __rest
 // src[(q*nprobe + j)*maxsplit + s] = partial row of pair (q, j) in split s, or -1.
 __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __restrict__ pos_of,
                                const int* __restrict__ p_off, const int* __restrict__ ubase,
-                               const int* __restrict__ nsl, int nlist, int64_t npairs, int maxsplit,
+                               const int* __restrict__ nsl, int nlist, int64_t npairs, int maxsplit, int wgs,
                                int* __restrict__ src) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < npairs;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int pos = pos_of[e];
         const int64_t l = coarse[e];
-        int ns = 0, first = 0, stride = 0;
+        int ns = 0, u0 = 0, r = 0, tiles2 = 0;
         if (pos >= 0 && l >= 0 && l < nlist) {
             ns = nsl[l];
             const int i = pos - p_off[l];
             const int m = p_off[l + 1] - p_off[l];
-            const int tiles2 = (((m + UNIT_ROWS - 1) / UNIT_ROWS) + 1) & ~1;
-            first = (ubase[l] + i / UNIT_ROWS) * UNIT_ROWS + (i % UNIT_ROWS);
-            stride = tiles2 * UNIT_ROWS;
+            tiles2 = (((m + UNIT_ROWS - 1) / UNIT_ROWS) + 1) & ~1;
+            u0 = ubase[l] + i / UNIT_ROWS;
+            r = i % UNIT_ROWS;
         }
+        // partial row of (unit u, warpgroup g, row r) = (u*wgs + g)*128 + r
         for (int s = 0; s < maxsplit; s++)
-            src[e * maxsplit + s] = (s < ns) ? first + s * stride : -1;
+            for (int g = 0; g < wgs; g++)
+                src[(e * maxsplit + s) * wgs + g] = (s < ns) ? ((u0 + s * tiles2) * wgs + g) * UNIT_ROWS + r : -1;
     }
 }
 
@@ -237,7 +263,7 @@ constexpr int IVF_CHUNK = 8192;  // item rows per unit inside one list (long run
 
 struct IvfPlan {
     int64_t npairs;
-    int maxsplit, max_units, grid;
+    int maxsplit, max_units, grid, wgs;
 };
 
 static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int path) {
@@ -247,6 +273,7 @@ static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int
     if (p.maxsplit < 1) p.maxsplit = 1;
     int64_t mu = (p.npairs / UNIT_ROWS + 2 * (int64_t)nlist) * p.maxsplit;
     p.max_units = (int)mu;
+    p.wgs = path == NRB_PATH_SIMT ? 1 : 2;
     p.grid = path == NRB_PATH_SIMT ? simt_grid(p.max_units) : tc_grid(p.max_units);
     return p;
 }
@@ -273,7 +300,7 @@ static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int
     w.ubase = c.take<int>(nlist + 1);
     w.nsl = c.take<int>(nlist);
     w.n_units = c.take<int>(1);
-    w.src = c.take<int>((size_t)p.npairs * p.maxsplit);
+    w.src = c.take<int>((size_t)p.npairs * p.maxsplit * p.wgs);
     w.units = c.take<Unit>(p.max_units);
     const size_t plane = (size_t)(p.npairs + UNIT_ROWS) * kp;
     if (path == NRB_PATH_SIMT) {
@@ -285,8 +312,8 @@ static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int
         w.g_lo = c.take<float>(plane);
     }
     w.g_norms = c.take<float>(p.npairs + UNIT_ROWS);
-    w.part_key = c.take<float>((size_t)p.max_units * UNIT_ROWS * k);
-    w.part_idx = c.take<int>((size_t)p.max_units * UNIT_ROWS * k);
+    w.part_key = c.take<float>((size_t)p.max_units * p.wgs * UNIT_ROWS * k);
+    w.part_idx = c.take<int>((size_t)p.max_units * p.wgs * UNIT_ROWS * k);
     w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(p.grid) : tc_scratch_bytes(p.grid);
     w.scratch = c.take<char>(w.scratch_bytes);
     w.total = c.off;
@@ -388,7 +415,8 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         return NRB_ERR_WORKSPACE;
     }
     int rc;
-    if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.nsplit, p.chunk_rows, st))) return rc;
+    if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.full_pairs, p.tail_pairs,
+                                     p.tsplit, p.chunk_rows, p.wgs, st))) return rc;
     if (path != NRB_PATH_TC1) {
         {
             ProfScope prof(st);
@@ -398,7 +426,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
                 rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
         }
         if (rc) return rc;
-        return launch_select(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, metric, nullptr, id_base, D, I, st);
+        return launch_select(w.part_key, w.part_idx, w.src, p.S, q->n, k, metric, nullptr, id_base, D, I, st);
     }
     // ---- 1xTF32 filter + exact refine, then the 3xTF32 kernel for whatever was flagged
     const int pw = k + TC1_EXTRA;
@@ -410,7 +438,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
                                  w.part_idx, w.flags, w.scratch, w.scratch_bytes, st);
     }
     if (rc) return rc;
-    if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.nsplit, q->n, k, pw, metric, q, b, eps_xmax,
+    if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
                                    id_base, w.flags, D, I, st))) return rc;
     if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
     int nflag = 0;
@@ -491,9 +519,9 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     int rc = require_device();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    path = resolve_path(path);
+    path = resolve_path(path);  // the list scan runs 3xTF32 (or SIMT); the 1xTF32 filter is flat-only
     const IvfPlan p = plan_ivf(q->n, nprobe, nlist, max_list_len, path);
-    NRB_REQUIRE((int64_t)nprobe * p.maxsplit <= 256, "ivf_search: nprobe*splits = %d > 256 merge sources", nprobe * p.maxsplit);
+    NRB_REQUIRE((int64_t)nprobe * p.maxsplit * p.wgs <= 256, "ivf_search: nprobe*splits = %d > 256 merge sources", nprobe * p.maxsplit * p.wgs);
     const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path);
     if (!workspace || workspace_bytes < w.total) {
         set_error("ivf_search: workspace %zu < %zu bytes", workspace_bytes, w.total);
@@ -509,7 +537,7 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     {
         int64_t blocks = (p.npairs + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        ivf_src_kernel<<<(unsigned)blocks, 256, 0, st>>>(coarse, w.pos_of, w.p_off, w.ubase, w.nsl, nlist, p.npairs, p.maxsplit, w.src);
+        ivf_src_kernel<<<(unsigned)blocks, 256, 0, st>>>(coarse, w.pos_of, w.p_off, w.ubase, w.nsl, nlist, p.npairs, p.maxsplit, p.wgs, w.src);
         NRB_LAUNCH_CHECK();
     }
     // 3. query rows in group order
@@ -545,7 +573,7 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
         prof.e1 = nullptr;
     }
     if (rc) return rc;
-    return launch_select(w.part_key, w.part_idx, w.src, nprobe * p.maxsplit, q->n, k, metric, ids, 0, D, I, st);
+    return launch_select(w.part_key, w.part_idx, w.src, nprobe * p.maxsplit * p.wgs, q->n, k, metric, ids, 0, D, I, st);
 }
 
 extern "C" int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed) {

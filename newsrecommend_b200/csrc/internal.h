@@ -61,7 +61,7 @@ int launch_compact_flags(const int* flags, int64_t n, int* list, int* count, cud
 int launch_scatter_results(const float* Df, const int64_t* If, const int* list, int n, int k, float* D,
                            int64_t* I, cudaStream_t st);
 int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
-                           int nsplit, int chunk_rows, cudaStream_t st);
+                           int full_pairs, int tail_pairs, int tsplit, int chunk_rows, int wgs, cudaStream_t st);
 size_t counting_sort_ws(int64_t n, int nb);
 int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets, int* order,
                              int* pos_of, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -478,33 +478,56 @@ __global__ void scatter_results_kernel(const float* __restrict__ Df, const int64
     }
 }
 
-// Units + src table of the flat search: unit u = s*nqt2 + t covers query tile t and item chunk
-// s (nqt2 = nqt rounded up to even; the odd tile out is a phantom unit with a_rows = 0, so that
-// units 2p and 2p+1 always share their item rows -- the CTA-pair kernel needs that).
-// Concurrently resident CTAs (consecutive u) share the chunk, so its tiles stay in L2.
+// Units + src table of the flat search (plan in api.cu: plan_flat). Pair p < full_pairs: units
+// 2p, 2p+1 = query tiles 2p, 2p+1 against the whole catalog. Tail pair j, chunk c: pair index
+// full_pairs + c*tail_pairs + j = query tiles 2(full_pairs + j) (+1) against item chunk c.
+// A unit whose query tile does not exist (odd tile count) is a phantom with a_rows = 0.
+// Partial row of (unit u, warpgroup g, row r) = (u*wgs + g)*128 + r.
 __global__ void fill_flat_units_kernel(Unit* __restrict__ units, int* __restrict__ n_units_out,
                                        int* __restrict__ src, int64_t nq, int64_t nb, int nqt,
-                                       int nsplit, int chunk_rows) {
+                                       int full_pairs, int tail_pairs, int tsplit, int chunk_rows, int wgs) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nqt2 = (nqt + 1) & ~1;
-    const int64_t nunits = (int64_t)nqt2 * nsplit;
+    const int64_t nunits = 2 * ((int64_t)full_pairs + (int64_t)tail_pairs * tsplit);
     if (tid == 0) *n_units_out = (int)nunits;
     if (tid < nunits) {
-        const int s = (int)(tid / nqt2), t = (int)(tid % nqt2);
+        const int pair = (int)(tid >> 1), r = (int)(tid & 1);
+        int t, c;  // query tile, item chunk (-1 = whole catalog)
+        if (pair < full_pairs) {
+            t = 2 * pair + r;
+            c = -1;
+        } else {
+            const int tp = pair - full_pairs;
+            c = tp / tail_pairs;
+            t = 2 * (full_pairs + tp % tail_pairs) + r;
+        }
         Unit u;
-        int64_t ar = nq - (int64_t)t * UNIT_ROWS;
+        const int64_t ar = nq - (int64_t)t * UNIT_ROWS;
         u.a_rows = t < nqt ? (int)(ar < UNIT_ROWS ? ar : UNIT_ROWS) : 0;
         u.a_row0 = t < nqt ? t * UNIT_ROWS : 0;
-        u.b_row0 = s * chunk_rows;
-        int64_t br = nb - (int64_t)s * chunk_rows;
-        u.b_rows = (int)(br < chunk_rows ? (br > 0 ? br : 0) : chunk_rows);
+        if (c < 0) {
+            u.b_row0 = 0;
+            u.b_rows = (int)nb;
+        } else {
+            u.b_row0 = c * chunk_rows;
+            const int64_t br = nb - (int64_t)c * chunk_rows;
+            u.b_rows = (int)(br < chunk_rows ? (br > 0 ? br : 0) : chunk_rows);
+        }
         units[tid] = u;
     }
-    const int64_t total = nq * nsplit;
+    const int S = tsplit * wgs;
+    const int64_t total = nq * S;
     for (int64_t e = tid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = e / nsplit;
-        const int s = (int)(e - q * nsplit);
-        src[e] = (int)(((int64_t)s * nqt2 + q / UNIT_ROWS) * UNIT_ROWS + q % UNIT_ROWS);
+        const int64_t q = e / S;
+        const int sl = (int)(e - q * S);
+        const int c = sl / wgs, g = sl - c * wgs;
+        const int t = (int)(q / UNIT_ROWS), pair = t >> 1, r = t & 1;
+        int64_t u = -1;
+        if (pair < full_pairs) {
+            if (c == 0) u = 2 * (int64_t)pair + r;
+        } else {
+            u = 2 * ((int64_t)full_pairs + (int64_t)c * tail_pairs + (pair - full_pairs)) + r;
+        }
+        src[e] = u < 0 ? -1 : (int)((u * wgs + g) * UNIT_ROWS + q % UNIT_ROWS);
     }
 }
 
@@ -582,14 +605,15 @@ int launch_scatter_results(const float* Df, const int64_t* If, const int* list, 
 }
 
 int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
-                           int nsplit, int chunk_rows, cudaStream_t st) {
-    const int64_t total = nq * nsplit;
-    int64_t nunits = (int64_t)((nqt + 1) & ~1) * nsplit;
-    int64_t work = total > nunits ? total : nunits;
-    int blocks = (int)((work + 255) / 256);
+                           int full_pairs, int tail_pairs, int tsplit, int chunk_rows, int wgs, cudaStream_t st) {
+    const int64_t total = nq * tsplit * wgs;
+    const int64_t nunits = 2 * ((int64_t)full_pairs + (int64_t)tail_pairs * tsplit);
+    int64_t blocks = (total + 255) / 256;
     if (blocks > 4096) blocks = 4096;
-    if (blocks < (nunits + 255) / 256) blocks = (int)((nunits + 255) / 256);
-    fill_flat_units_kernel<<<blocks, 256, 0, st>>>(units, n_units_out, src, nq, nb, nqt, nsplit, chunk_rows);
+    if (blocks < (nunits + 255) / 256) blocks = (nunits + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    fill_flat_units_kernel<<<(unsigned)blocks, 256, 0, st>>>(units, n_units_out, src, nq, nb, nqt, full_pairs,
+                                                             tail_pairs, tsplit, chunk_rows, wgs);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

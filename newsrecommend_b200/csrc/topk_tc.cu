@@ -10,12 +10,15 @@
 //                     of 32 fp32 (128-byte swizzled rows), mbarrier ring
 //   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
 //                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
-//   warps 2-5         epilogue: tcgen05.ld the 128 x 256 accumulator (one query row per thread),
-//                     turn scores into keys, append everything above the row's running
+//   warps 2-5, 6-9    two epilogue warpgroups; warpgroup g owns TMEM accumulator g, i.e. every
+//                     second tile: tcgen05.ld the 128 x 256 accumulator (one query row per
+//                     thread), turn scores into keys, append everything above the row's running
 //                     threshold to the row's candidate buffer; a warp-cooperative bitonic
 //                     prune brings a full buffer back to the best k and raises the threshold.
-// TMEM holds two accumulators (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of
-// tile t+1. The score matrix never exists in HBM.
+//                     Each warpgroup keeps its own per-row state and writes its own partial
+//                     rows (merged later by the k-way merge).
+// TMEM holds two accumulators (2 x 256 columns) so the epilogues overlap the MMAs of the next
+// tiles. The score matrix never exists in HBM.
 //
 // Two variants share the epilogue:
 //   v2 (default)  CTA pairs, tcgen05.mma.cta_group::2 with M = 256: the two CTAs of a cluster
@@ -42,7 +45,8 @@ constexpr int KC = 32;    // fp32 elements per K chunk (128-byte swizzle span)
 constexpr int A_BYTES = BM * KC * 4;        // 16 KB: 128 rows x 128 B
 constexpr int BH_BYTES = (BN / 2) * KC * 4; // 16 KB: half item tile (v2)
 constexpr int B_BYTES = BN * KC * 4;        // 32 KB: full item tile (v1)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups of 4 warps
+constexpr int EPI_WGS = 2;
 constexpr int TMEM_COLS = 512;
 
 constexpr int V1_STAGES = 2;
@@ -79,13 +83,13 @@ struct EpiRow {
 //   id0     item row index of column 0
 //   nrm     item norms of the tile in shared memory (L2 only)
 //   ck/ci   candidate buffers of this warp's 32 rows; myk/myi = this lane's row
-template <bool L2>
+template <bool L2, bool FULL>
 __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
                                          float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                          int lane) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (c0 >= valid) break;  // warp-uniform
+        if (!FULL && c0 >= valid) break;  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
         ptx::tmem_ld_wait();
@@ -95,7 +99,7 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
         for (int i = 0; i < 32; i++) {
             float x = __uint_as_float(v[i]);
             if (L2) x = -fmaxf(st.qn + nrm[c0 + i] - 2.f * x, 0.f);
-            if (c0 + i >= valid) x = NEG_INF;
+            if (!FULL && c0 + i >= valid) x = NEG_INF;
             f[i] = x;
             m = fmaxf(m, x);
         }
@@ -131,12 +135,12 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
 
 // Unit finished: the warp's 32 rows, best-first, into the unit's partial rows (`pw` entries
 // per row: the best k plus, for the margin filter, everything within the margin of the k-th).
-__device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int u, int quad, int k, int pw,
+__device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int64_t prow0, int k, int pw,
                                              float* part_key, int* part_idx, int lane) {
     for (int src = 0; src < 32; src++) {
         const int n = __shfl_sync(0xffffffffu, st.cnt, src);
         const float mg = __shfl_sync(0xffffffffu, st.margin, src);
-        const int64_t o = ((int64_t)u * UNIT_ROWS + quad * 32 + src) * pw;
+        const int64_t o = (prow0 + src) * pw;
         int kept;
         bool ovf;
         warp_prune_row_m(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, mg, pw, pw,
@@ -147,14 +151,97 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
 
 template <bool L2>
 __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
-                                                int valid, int64_t b_total, int etid) {
+                                                int valid, int64_t b_total, int etid, int wg) {
     if (L2) {
-        // stage the tile's item norms; the named barrier also orders reuse of the buffer
+        // stage the tile's item norms; the warpgroup's named barrier also orders reuse of the buffer
         for (int c = etid; c < BN; c += 128) {
             const int64_t br = (int64_t)un.b_row0 + col_base + c;
             nrm[c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (wg == 0)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        else
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+}
+
+// The selection epilogue shared by the three kernels. Executed by warps 2..9; warpgroup
+// g = (warp-2)/4 handles the tiles whose running index (over all units of this CTA) has parity
+// g, i.e. TMEM accumulator g. PAIR: units are taken in CTA pairs and the accumulator is handed
+// back with a cluster-scope arrive on the leader's barrier.
+struct EpiArgs {
+    const Unit* units;
+    int n_units, k, pw;
+    float margin_scale;  // 0: plain top-k (3xTF32 kernels)
+    const float *a_norms, *b_norms;
+    int64_t a_total, b_total;
+    float* part_key;
+    int* part_idx;
+    int* row_flags;
+    float* cand_key_buf;
+    int* cand_idx_buf;
+};
+
+template <bool L2, bool PAIR, bool NEED_QN>
+__device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty, float (*nrm)[BN],
+                                             uint32_t tmem_base, int warp, int lane, uint32_t rank) {
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;         // TMEM lane quarter this warp may read
+    const int row = quad * 32 + lane;  // query row inside the tile
+    const int etid = ((warp - 2) & 3) * 32 + lane;
+    const int64_t crow0 = ((int64_t)blockIdx.x * EPI_WGS + wg) * BM + quad * 32;  // this warp's 32 buffer rows
+    float* ck = A.cand_key_buf + crow0 * CAND_CAP;
+    int* ci = A.cand_idx_buf + crow0 * CAND_CAP;
+    float* myk = ck + (int64_t)lane * CAND_CAP;
+    int* myi = ci + (int64_t)lane * CAND_CAP;
+    uint32_t tempty_remote[2] = {0, 0};
+    if (PAIR) {
+        tempty_remote[0] = ptx::mapa_u32(&tempty[0], 0);
+        tempty_remote[1] = ptx::mapa_u32(&tempty[1], 0);
+    }
+    const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int count = PAIR ? (A.n_units + 1) >> 1 : A.n_units;
+    uint32_t gt = 0;  // running tile index of this CTA (same sequence as the MMA warp)
+    for (int i = first; i < count; i += stride) {
+        const int u = PAIR ? 2 * i + (int)rank : i;
+        const Unit un = A.units[u];
+        const int ntiles = (PAIR || un.a_rows > 0) ? (un.b_rows + BN - 1) / BN : 0;
+        const int64_t ar = (int64_t)un.a_row0 + row;
+        const bool live = row < un.a_rows && ar < A.a_total;
+        EpiRow st;
+        st.cnt = 0;
+        st.thr = live ? NEG_INF : __builtin_huge_valf();
+        st.qn = ((L2 || NEED_QN) && live) ? A.a_norms[ar] : 0.f;
+        st.margin = NEED_QN ? A.margin_scale * sqrtf(st.qn) * (L2 ? 2.f : 1.f) : 0.f;
+        st.flag = 0;
+        for (int t = 0; t < ntiles; t++, gt++) {
+            if ((int)(gt & 1) != wg) continue;  // the other warpgroup's accumulator
+            const int acc = wg;
+            const uint32_t acc_phase = (gt >> 1) & 1;
+            const int col_base = t * BN;
+            const int valid = un.b_rows - col_base;
+            epi_stage_norms<L2>(nrm[acc], A.b_norms, un, col_base, valid, A.b_total, etid, wg);
+            ptx::mbar_wait(&tfull[acc], acc_phase);
+            ptx::tcgen05_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+            if (valid >= BN)
+                epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm[acc], st, ck, ci, myk, myi, A.k, A.pw, lane);
+            else
+                epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm[acc], st, ck, ci, myk, myi, A.k, A.pw, lane);
+            // accumulator drained: hand it back to the MMA warp
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR)
+                    ptx::mbar_arrive_cluster(tempty_remote[acc]);
+                else
+                    ptx::mbar_arrive(&tempty[acc]);
+            }
+        }
+        epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
+                     A.part_idx, lane);
+        if (NEED_QN && st.flag && live) A.row_flags[ar] = 1;
     }
 }
 
@@ -272,44 +359,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
     } else {
         // ------------------------------------------------------------------ selection epilogue
-        const int quad = warp & 3;            // TMEM lane quarter this warp may read
-        const int row = quad * 32 + lane;     // query row inside the tile
-        const int etid = (warp - 2) * 32 + lane;
-        float* ck = cand_key_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;  // warp's 32 rows
-        int* ci = cand_idx_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
-        float* myk = ck + (int64_t)lane * CAND_CAP;
-        int* myi = ci + (int64_t)lane * CAND_CAP;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const Unit un = units[u];
-            const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
-            EpiRow st;
-            st.cnt = 0;
-            st.thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
-            st.qn = 0.f;
-            st.margin = 0.f;
-            st.flag = 0;
-            if (L2) {
-                const int64_t ar = (int64_t)un.a_row0 + row;
-                st.qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
-            }
-            for (int t = 0; t < ntiles; t++) {
-                const int col_base = t * BN;
-                const int valid = un.b_rows - col_base;
-                epi_stage_norms<L2>(sh->nrm[acc], b_norms, un, col_base, valid, b_total, etid);
-                ptx::mbar_wait(&sh->tfull[acc], acc_phase);
-                ptx::tcgen05_fence_after();
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, k, lane);
-                ptx::tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&sh->tempty[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
-            epi_unit_end(st, ck, ci, u, quad, k, k, part_key, part_idx, lane);
-        }
+        EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
+                   cand_key_buf, cand_idx_buf};
+        epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, 0);
     }
 
     ptx::tcgen05_fence_before();
@@ -441,46 +493,9 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
     } else {
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const int etid = (warp - 2) * 32 + lane;
-        float* ck = cand_key_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
-        int* ci = cand_idx_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
-        float* myk = ck + (int64_t)lane * CAND_CAP;
-        int* myi = ci + (int64_t)lane * CAND_CAP;
-        const uint32_t tempty0[2] = {ptx::mapa_u32(&sh->tempty[0], 0), ptx::mapa_u32(&sh->tempty[1], 0)};
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
-            const int u = 2 * p + (int)rank;
-            const Unit un = units[u];
-            const int ntiles = (un.b_rows + BN - 1) / BN;
-            EpiRow st;
-            st.cnt = 0;
-            st.thr = (row < un.a_rows) ? NEG_INF : __builtin_huge_valf();
-            st.qn = 0.f;
-            st.margin = 0.f;
-            st.flag = 0;
-            if (L2) {
-                const int64_t ar = (int64_t)un.a_row0 + row;
-                st.qn = (row < un.a_rows && ar < a_total) ? a_norms[ar] : 0.f;
-            }
-            for (int t = 0; t < ntiles; t++) {
-                const int col_base = t * BN;
-                const int valid = un.b_rows - col_base;
-                epi_stage_norms<L2>(sh->nrm[acc], b_norms, un, col_base, valid, b_total, etid);
-                ptx::mbar_wait(&sh->tfull[acc], acc_phase);
-                ptx::tcgen05_fence_after();
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, k, lane);
-                ptx::tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(tempty0[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
-            epi_unit_end(st, ck, ci, u, quad, k, k, part_key, part_idx, lane);
-        }
+        EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
+                   cand_key_buf, cand_idx_buf};
+        epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
     }
 
     ptx::tcgen05_fence_before();
@@ -638,45 +653,9 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
     } else {
         // ------------------------------------------------------------------ filter epilogue (both CTAs)
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const int etid = (warp - 2) * 32 + lane;
-        float* ck = cand_key_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
-        int* ci = cand_idx_buf + ((int64_t)blockIdx.x * BM + quad * 32) * CAND_CAP;
-        float* myk = ck + (int64_t)lane * CAND_CAP;
-        int* myi = ci + (int64_t)lane * CAND_CAP;
-        const uint32_t tempty0[2] = {ptx::mapa_u32(&sh->tempty[0], 0), ptx::mapa_u32(&sh->tempty[1], 0)};
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
-            const int u = 2 * p + (int)rank;
-            const Unit un = units[u];
-            const int ntiles = (un.b_rows + BN - 1) / BN;
-            const int64_t ar = (int64_t)un.a_row0 + row;
-            const bool live = row < un.a_rows && ar < a_total;
-            EpiRow st;
-            st.cnt = 0;
-            st.thr = live ? NEG_INF : __builtin_huge_valf();
-            st.qn = live ? a_norms[ar] : 0.f;
-            st.margin = margin_scale * sqrtf(st.qn) * (L2 ? 2.f : 1.f);
-            st.flag = 0;
-            for (int t = 0; t < ntiles; t++) {
-                const int col_base = t * BN;
-                const int valid = un.b_rows - col_base;
-                epi_stage_norms<L2>(sh->nrm[acc], b_norms, un, col_base, valid, b_total, etid);
-                ptx::mbar_wait(&sh->tfull[acc], acc_phase);
-                ptx::tcgen05_fence_after();
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                epi_tile<L2>(taddr0, valid, un.b_row0 + col_base, sh->nrm[acc], st, ck, ci, myk, myi, k, pw, lane);
-                ptx::tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(tempty0[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
-            epi_unit_end(st, ck, ci, u, quad, k, pw, part_key, part_idx, lane);
-            if (st.flag && live) row_flags[ar] = 1;
-        }
+        EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
+                   row_flags, cand_key_buf, cand_idx_buf};
+        epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
     }
 
     ptx::tcgen05_fence_before();
@@ -762,7 +741,7 @@ int tc_grid(int n_units) {
 }
 
 size_t tc_scratch_bytes(int grid) {
-    return (size_t)grid * BM * CAND_CAP * (sizeof(float) + sizeof(int)) + 256;
+    return (size_t)grid * EPI_WGS * BM * CAND_CAP * (sizeof(float) + sizeof(int)) + 256;
 }
 
 int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
@@ -785,7 +764,7 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
     if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, v == 1 ? BN : BN / 2))) return rc;
     if ((rc = make_plane_map(&mbl, b->lo, b->n, b->kp, v == 1 ? BN : BN / 2))) return rc;
     float* ck = (float*)scratch;
-    int* ci = (int*)((char*)scratch + (size_t)grid * BM * CAND_CAP * sizeof(float));
+    int* ci = (int*)((char*)scratch + (size_t)grid * EPI_WGS * BM * CAND_CAP * sizeof(float));
     const int nkc = a->kp / KC;
 #define NRB_TC_LAUNCH(KERNEL, SMEM)                                                                          \
     do {                                                                                                     \
@@ -830,7 +809,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
     if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
     if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN / 2))) return rc;
     float* ck = (float*)scratch;
-    int* ci = (int*)((char*)scratch + (size_t)grid * BM * CAND_CAP * sizeof(float));
+    int* ci = (int*)((char*)scratch + (size_t)grid * EPI_WGS * BM * CAND_CAP * sizeof(float));
     const int nkc = a->kp / KC;
     if (metric == NRB_METRIC_L2) {
         NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
