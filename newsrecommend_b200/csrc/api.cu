@@ -131,6 +131,7 @@ struct FlatWs {
     float* part_key;
     int* part_idx;
     int *flags, *flag_list, *flag_count;  // NRB_PATH_TC1 only
+    unsigned* gthr;                       // per-query shared bounds (tcgen05 paths)
     void* scratch;
     size_t scratch_bytes;
     size_t total;
@@ -146,6 +147,7 @@ static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int pat
     w.part_key = c.take<float>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
     w.part_idx = c.take<int>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
     w.flags = w.flag_list = w.flag_count = nullptr;
+    w.gthr = path == NRB_PATH_SIMT ? nullptr : c.take<unsigned>(nq);
     if (path == NRB_PATH_TC1) {
         w.flags = c.take<int>(nq);
         w.flag_list = c.take<int>(nq);
@@ -282,6 +284,7 @@ struct IvfWs {
     void* cs;
     size_t cs_bytes;
     int *p_off, *order, *pos_of, *ubase, *nsl, *n_units, *src;
+    unsigned* gthr;
     Unit* units;
     float *g_raw, *g_hi, *g_lo, *g_norms, *part_key;
     int* part_idx;
@@ -289,9 +292,10 @@ struct IvfWs {
     size_t scratch_bytes, total;
 };
 
-static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int path) {
+static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int path, int64_t nq) {
     Carver c(ws);
     IvfWs w;
+    w.gthr = path == NRB_PATH_SIMT ? nullptr : c.take<unsigned>(nq);
     w.cs_bytes = counting_sort_ws(p.npairs, nlist);
     w.cs = c.take<char>(w.cs_bytes);
     w.p_off = c.take<int>(nlist + 2);
@@ -417,13 +421,15 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     int rc;
     if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.full_pairs, p.tail_pairs,
                                      p.tsplit, p.chunk_rows, p.wgs, st))) return rc;
+    if (w.gthr) NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
     if (path != NRB_PATH_TC1) {
         {
             ProfScope prof(st);
             if (path == NRB_PATH_SIMT)
                 rc = launch_topk_simt_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
             else
-                rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+                rc = launch_topk_tc_dev(q, b, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch,
+                                        w.scratch_bytes, w.gthr, nullptr, 1, st);
         }
         if (rc) return rc;
         return launch_select(w.part_key, w.part_idx, w.src, p.S, q->n, k, metric, nullptr, id_base, D, I, st);
@@ -435,7 +441,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     {
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
-                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, st);
+                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, st);
     }
     if (rc) return rc;
     if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
@@ -499,8 +505,8 @@ extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k
     if (nq <= 0 || nprobe <= 0 || k <= 0) return 256;
     IvfPlan p1 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_TC);
     IvfPlan p2 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_SIMT);
-    size_t a = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC).total;
-    size_t b = carve_ivf(nullptr, p2, nlist, k, kp, NRB_PATH_SIMT).total;
+    size_t a = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC, nq).total;
+    size_t b = carve_ivf(nullptr, p2, nlist, k, kp, NRB_PATH_SIMT, nq).total;
     return (a > b ? a : b) + 256;
 }
 
@@ -522,7 +528,7 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     path = resolve_path(path);  // the list scan runs 3xTF32 (or SIMT); the 1xTF32 filter is flat-only
     const IvfPlan p = plan_ivf(q->n, nprobe, nlist, max_list_len, path);
     NRB_REQUIRE((int64_t)nprobe * p.maxsplit * p.wgs <= 256, "ivf_search: nprobe*splits = %d > 256 merge sources", nprobe * p.maxsplit * p.wgs);
-    const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path);
+    const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path, q->n);
     if (!workspace || workspace_bytes < w.total) {
         set_error("ivf_search: workspace %zu < %zu bytes", workspace_bytes, w.total);
         return NRB_ERR_WORKSPACE;
@@ -566,8 +572,13 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     ProfScope prof(st);
     if (path == NRB_PATH_SIMT)
         rc = launch_topk_simt_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
-    else
-        rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+    else {
+        // all nprobe units of a query share one running bound: row p of the regrouped plane is
+        // pair order[p], i.e. query order[p] / nprobe
+        NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
+        rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch,
+                                w.scratch_bytes, w.gthr, w.order, nprobe, st);
+    }
     if (prof.e1) {
         cudaEventRecord(prof.e1, st);
         prof.e1 = nullptr;

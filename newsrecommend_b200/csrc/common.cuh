@@ -60,6 +60,16 @@ __device__ __forceinline__ float cand_key(uint64_t c) {
 __device__ __forceinline__ int cand_idx(uint64_t c) {
     return (int)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFu));
 }
+// Monotone float -> uint map (0 is below every float, including -inf): shared running bounds are
+// raised with atomicMax on this encoding.
+__device__ __forceinline__ uint32_t ordered_u32(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_u32(uint32_t u) {
+    if (u == 0) return NEG_INF;
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
 // The empty candidate: (-inf, idx -1) packs below every real candidate.
 __device__ __forceinline__ uint64_t empty_cand() { return pack_cand(NEG_INF, -1); }
 
@@ -115,7 +125,8 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
 // top-k prune. All 32 lanes must call with identical arguments.
 __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi, int n, int k, float margin,
                                                   int keep_max, int width, float* ok, int* oi, int lane,
-                                                  int* kept, bool* overflow) {
+                                                  int* kept, bool* overflow, float floor_thr = NEG_INF,
+                                                  float* kth_out = nullptr) {
     constexpr int R = CAND_CAP / 32;
     uint64_t c[R];
 #pragma unroll
@@ -131,7 +142,10 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
     for (int i = 0; i < R; i++)
         if (i == ki) kth = cand_key(c[i]);
     kth = __shfl_sync(0xffffffffu, kth, kl);
-    const float thr = kth - margin;  // NEG_INF stays NEG_INF
+    if (kth_out) *kth_out = kth;
+    // floor_thr: a threshold already known from elsewhere (the query's shared bound); entries
+    // at or below it can never reach the final top-k
+    const float thr = fmaxf(kth - margin, floor_thr);  // NEG_INF stays NEG_INF
     int cnt = 0;
 #pragma unroll
     for (int i = 0; i < R; i++) {
@@ -140,8 +154,10 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    const int base = n < k ? n : k;
-    cnt = cnt > base ? cnt : base;
+    if (floor_thr == NEG_INF) {
+        const int base = n < k ? n : k;  // without a floor the best min(n, k) always stay
+        cnt = cnt > base ? cnt : base;
+    }
     *overflow = cnt > keep_max;
     cnt = cnt > keep_max ? keep_max : cnt;
     *kept = cnt;

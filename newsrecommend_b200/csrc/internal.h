@@ -26,9 +26,12 @@ int tc_available();  // 1 when the current device is sm_100
 size_t tc_scratch_bytes(int grid);
 int tc_grid(int n_units_upper);
 void tc_set_variant(int v);  // 1 = single-CTA kernel, 2 = CTA-pair kernel (default)
+// gthr (optional): zero-initialised per-query shared bounds; row_map/row_div map query-side rows
+// to queries (null = identity).
 int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                        const int* n_units_dev, int grid, int metric, int k, float* part_key,
-                       int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st);
+                       int* part_idx, void* scratch, size_t scratch_bytes, unsigned* gthr,
+                       const int* row_map, int row_div, cudaStream_t st);
 
 // 1xTF32 filter + exact refine (NRB_PATH_TC1): partial rows are `pw` = k + TC1_EXTRA wide and hold
 // every candidate within the error margin of the k-th; row_flags[a_row] = 1 marks rows whose
@@ -39,7 +42,7 @@ int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
-                        size_t scratch_bytes, cudaStream_t st);
+                        size_t scratch_bytes, unsigned* gthr, cudaStream_t st);
 
 // ---- topk_simt.cu: fp32 CUDA-core distance + selection over the same Unit list
 size_t simt_scratch_bytes(int grid);

@@ -62,7 +62,7 @@ struct TcShared {
     uint64_t tempty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[2][BN];
+    float nrm[2][2][BN];  // [warpgroup][its own tile parity]: staged item norms (L2)
 };
 
 constexpr size_t V1_SMEM = (size_t)V1_STAGES * V1_STAGE_BYTES + sizeof(TcShared<V1_STAGES>) + 1024;
@@ -75,6 +75,7 @@ struct EpiRow {
     float qn;      // squared query norm (L2 keys, margins)
     float margin;  // 0 for the 3xTF32 kernels; error margin of the 1xTF32 filter
     int flag;      // set when more than keep_max candidates fell inside the margin
+    unsigned* gslot;  // the query's shared running lower bound of its k-th key (ordered uint), or null
 };
 
 // One 128 x 256 accumulator: thread = query row, 8 chunks of 32 columns.
@@ -119,15 +120,19 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
             need &= need - 1;
             const int n = __shfl_sync(0xffffffffu, st.cnt, src);
             const float mg = __shfl_sync(0xffffffffu, st.margin, src);
+            const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
             float* rk = ck + (int64_t)src * CAND_CAP;
             int* ri = ci + (int64_t)src * CAND_CAP;
             int kept;
             bool ovf;
-            const float tnew = warp_prune_row_m(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, lane, &kept, &ovf);
+            float kth;
+            const float tnew = warp_prune_row_m(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, lane, &kept, &ovf,
+                                                fl, &kth);
             if (lane == src) {
                 st.cnt = kept;
                 st.thr = tnew;
                 st.flag |= ovf ? 1 : 0;
+                if (st.gslot && kth > NEG_INF) atomicMax(st.gslot, ordered_u32(kth));
             }
         }
     }
@@ -140,12 +145,17 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
     for (int src = 0; src < 32; src++) {
         const int n = __shfl_sync(0xffffffffu, st.cnt, src);
         const float mg = __shfl_sync(0xffffffffu, st.margin, src);
+        const float fl = __shfl_sync(0xffffffffu, st.thr, src);
         const int64_t o = (prow0 + src) * pw;
         int kept;
         bool ovf;
+        float kth;
         warp_prune_row_m(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, mg, pw, pw,
-                         part_key + o, part_idx + o, lane, &kept, &ovf);
-        if (lane == src) st.flag |= ovf ? 1 : 0;
+                         part_key + o, part_idx + o, lane, &kept, &ovf, fl < __builtin_huge_valf() ? fl : NEG_INF, &kth);
+        if (lane == src) {
+            st.flag |= ovf ? 1 : 0;
+            if (st.gslot && kth > NEG_INF) atomicMax(st.gslot, ordered_u32(kth));
+        }
     }
 }
 
@@ -180,11 +190,19 @@ struct EpiArgs {
     int* row_flags;
     float* cand_key_buf;
     int* cand_idx_buf;
+    // Shared running bounds: gthr[query] (zero-initialised ordered uints) is raised by every
+    // unit of the query and read back at each tile, so units that start later (IVF lists, tail
+    // chunks, the second warpgroup) begin with a hot threshold instead of re-discovering it.
+    // Query of query-side row r: row_map ? row_map[r] / row_div : r.
+    unsigned* gthr;
+    const int* row_map;
+    int row_div;
 };
 
 template <bool L2, bool PAIR, bool NEED_QN>
-__device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty, float (*nrm)[BN],
-                                             uint32_t tmem_base, int warp, int lane, uint32_t rank) {
+__device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
+                                             float (*nrm)[2][BN], uint32_t tmem_base, int warp, int lane,
+                                             uint32_t rank) {
     const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;         // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;  // query row inside the tile
@@ -215,20 +233,29 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         st.qn = ((L2 || NEED_QN) && live) ? A.a_norms[ar] : 0.f;
         st.margin = NEED_QN ? A.margin_scale * sqrtf(st.qn) * (L2 ? 2.f : 1.f) : 0.f;
         st.flag = 0;
+        st.gslot = nullptr;
+        if (A.gthr && live) st.gslot = A.gthr + (A.row_map ? A.row_map[ar] / A.row_div : (int)ar);
         for (int t = 0; t < ntiles; t++, gt++) {
             if ((int)(gt & 1) != wg) continue;  // the other warpgroup's accumulator
+            if (st.gslot) {  // pick up what the query's other units have established so far
+                const float g = from_ordered_u32(*(volatile unsigned*)st.gslot);
+                st.thr = fmaxf(st.thr, g - st.margin);
+            }
             const int acc = wg;
             const uint32_t acc_phase = (gt >> 1) & 1;
             const int col_base = t * BN;
             const int valid = un.b_rows - col_base;
-            epi_stage_norms<L2>(nrm[acc], A.b_norms, un, col_base, valid, A.b_total, etid, wg);
+            // two norm buffers per warpgroup: a fast warp may stage tile n+1 of this warpgroup
+            // while a slow one still reads tile n (the named barrier keeps them within one tile)
+            float* nrm_t = nrm[wg][acc_phase];
+            epi_stage_norms<L2>(nrm_t, A.b_norms, un, col_base, valid, A.b_total, etid, wg);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
             if (valid >= BN)
-                epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm[acc], st, ck, ci, myk, myi, A.k, A.pw, lane);
+                epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
             else
-                epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm[acc], st, ck, ci, myk, myi, A.k, A.pw, lane);
+                epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
             // accumulator drained: hand it back to the MMA warp
             ptx::tcgen05_fence_before();
             __syncwarp();
@@ -254,7 +281,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                const float* __restrict__ a_norms, const float* __restrict__ b_norms,
                int64_t a_total, int64_t b_total, float* __restrict__ part_key,
                int* __restrict__ part_idx, float* __restrict__ cand_key_buf,
-               int* __restrict__ cand_idx_buf) {
+               int* __restrict__ cand_idx_buf, unsigned* __restrict__ gthr, const int* __restrict__ row_map,
+               int row_div) {
     constexpr int STAGES = V1_STAGES, STAGE_BYTES = V1_STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -360,7 +388,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     } else {
         // ------------------------------------------------------------------ selection epilogue
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
-                   cand_key_buf, cand_idx_buf};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, 0);
     }
 
@@ -383,7 +411,8 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 const float* __restrict__ a_norms, const float* __restrict__ b_norms,
                 int64_t a_total, int64_t b_total, float* __restrict__ part_key,
                 int* __restrict__ part_idx, float* __restrict__ cand_key_buf,
-                int* __restrict__ cand_idx_buf) {
+                int* __restrict__ cand_idx_buf, unsigned* __restrict__ gthr, const int* __restrict__ row_map,
+                int row_div) {
     constexpr int STAGES = V2_STAGES, STAGE_BYTES = V2_STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -494,7 +523,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     } else {
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
-                   cand_key_buf, cand_idx_buf};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
     }
 
@@ -530,7 +559,7 @@ struct Tc3Shared {
     uint64_t aempty;
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[2][BN];
+    float nrm[2][2][BN];
 };
 constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared) + 1024;
 
@@ -540,7 +569,8 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc, int k, int pw,
                 float margin_scale, const float* __restrict__ a_norms, const float* __restrict__ b_norms,
                 int64_t a_total, int64_t b_total, float* __restrict__ part_key, int* __restrict__ part_idx,
-                int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf) {
+                int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf,
+                unsigned* __restrict__ gthr) {
     constexpr int STAGES = V3_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -654,7 +684,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     } else {
         // ------------------------------------------------------------------ filter epilogue (both CTAs)
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   row_flags, cand_key_buf, cand_idx_buf};
+                   row_flags, cand_key_buf, cand_idx_buf, gthr, nullptr, 1};
         epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
     }
 
@@ -746,7 +776,8 @@ size_t tc_scratch_bytes(int grid) {
 
 int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                        const int* n_units_dev, int grid, int metric, int k, float* part_key,
-                       int* part_idx, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                       int* part_idx, void* scratch, size_t scratch_bytes, unsigned* gthr,
+                       const int* row_map, int row_div, cudaStream_t st) {
     NRB_REQUIRE(a->hi && a->lo && b->hi && b->lo, "tc: hi/lo planes required");
     NRB_REQUIRE(a->kp == b->kp && a->kp % KC == 0 && a->kp >= KC, "tc: kp mismatch / not a multiple of %d", KC);
     NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "tc: k=%d out of range [1,%d]", k, NRB_MAX_K);
@@ -770,7 +801,8 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
     do {                                                                                                     \
         NRB_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
         KERNEL<<<grid, NUM_THREADS, SMEM, st>>>(mah, mal, mbh, mbl, units, n_units_dev, nkc, k, a->norms,     \
-                                                b->norms, a->n, b->n, part_key, part_idx, ck, ci);           \
+                                                b->norms, a->n, b->n, part_key, part_idx, ck, ci, gthr,     \
+                                                row_map, row_div);                                           \
     } while (0)
     if (v == 1) {
         if (metric == NRB_METRIC_L2)
@@ -796,7 +828,7 @@ int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
-                        size_t scratch_bytes, cudaStream_t st) {
+                        size_t scratch_bytes, unsigned* gthr, cudaStream_t st) {
     NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", 128 - TC1_EXTRA);
     NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - 64, "tc1: bad kp / pw");
     NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
@@ -815,12 +847,12 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
         NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
         topk_tc3_kernel<true><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
                                                                   a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                  row_flags, ck, ci);
+                                                                  row_flags, ck, ci, gthr);
     } else {
         NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
         topk_tc3_kernel<false><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
                                                                    a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                   row_flags, ck, ci);
+                                                                   row_flags, ck, ci, gthr);
     }
     NRB_LAUNCH_CHECK();
     return NRB_OK;
