@@ -143,21 +143,27 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
         if (i == ki) kth = cand_key(c[i]);
     kth = __shfl_sync(0xffffffffu, kth, kl);
     if (kth_out) *kth_out = kth;
-    // floor_thr: a threshold already known from elsewhere (the query's shared bound); entries
-    // at or below it can never reach the final top-k
-    const float thr = fmaxf(kth - margin, floor_thr);  // NEG_INF stays NEG_INF
-    int cnt = 0;
+    // Keep (a prefix of the sorted entries): the best k plus everything within `margin` of the
+    // k-th, but nothing below floor_thr -- a bound already established elsewhere (the query's
+    // shared bound minus margin, or this row's previous threshold). The floor is NON-strict:
+    // the row's own k-th entry has key == its threshold and must survive.
+    const float thr = kth - margin;  // NEG_INF stays NEG_INF
+    int c_thr = 0, c_floor = 0;
 #pragma unroll
     for (int i = 0; i < R; i++) {
         const int e = i * 32 + lane;
-        cnt += (e < n && cand_key(c[i]) > thr) ? 1 : 0;
+        const float key = cand_key(c[i]);
+        c_thr += (e < n && key > thr) ? 1 : 0;
+        c_floor += (e < n && key >= floor_thr) ? 1 : 0;
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (floor_thr == NEG_INF) {
-        const int base = n < k ? n : k;  // without a floor the best min(n, k) always stay
-        cnt = cnt > base ? cnt : base;
+    for (int o = 16; o >= 1; o >>= 1) {
+        c_thr += __shfl_xor_sync(0xffffffffu, c_thr, o);
+        c_floor += __shfl_xor_sync(0xffffffffu, c_floor, o);
     }
+    const int base = n < k ? n : k;
+    int cnt = c_thr > base ? c_thr : base;
+    cnt = cnt < c_floor ? cnt : c_floor;
     *overflow = cnt > keep_max;
     cnt = cnt > keep_max ? keep_max : cnt;
     *kept = cnt;
@@ -171,7 +177,7 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
         }
     }
     __syncwarp();
-    return thr;
+    return fmaxf(thr, floor_thr);  // threshold for further appends
 }
 
 // Plain top-k prune (margin 0): keeps min(n, k) entries, returns kth.
