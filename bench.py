@@ -166,14 +166,14 @@ def run_reference(args):
     v = n * steps / dt
     sample = (f"each step = first {n} of {NQ} queries against the full catalog; faiss is not installable here, "
               f"this is the faiss-equivalent oracle port on all {cores} host threads")
-    print(json.dumps({
+    args.out.emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_per_step": n, "k": K},
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def run_ours(args):
@@ -309,10 +309,24 @@ def run_ours(args):
         }
         if world == 1 and not os.environ.get("NRB_BENCH_SKIP_CPU"):  # skipped only for ncu captures
             out["cpu_baseline"] = cpu_baseline(xb, xq)
-        print(json.dumps(out))
+        args.out.emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class _StdoutGuard:
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON
+    line on stdout. Route fd 1 to stderr for the whole run and emit the JSON on the saved fd."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(obj) + "\n").encode())
 
 
 def main():
@@ -325,6 +339,7 @@ def main():
                     help="auto/tc1 = 1xTF32 filter + exact refine (default), tc = 3xTF32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.out = _StdoutGuard()
     if args.impl == "reference":
         run_reference(args)
     else:

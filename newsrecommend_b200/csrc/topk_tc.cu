@@ -94,25 +94,32 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
         ptx::tmem_ld_wait();
+        // Branch-free pass mask (bit i: column c0+i beats the row's threshold). A warp-chunk of
+        // 1,024 scores nearly always holds a few candidates, so there is no cheap "nothing to
+        // do" exit; what matters is that the common work is straight-line code.
         float f[32];
-        float m = NEG_INF;
+        uint32_t mask = 0;
 #pragma unroll
         for (int i = 0; i < 32; i++) {
             float x = __uint_as_float(v[i]);
             if (L2) x = -fmaxf(st.qn + nrm[c0 + i] - 2.f * x, 0.f);
             if (!FULL && c0 + i >= valid) x = NEG_INF;
             f[i] = x;
-            m = fmaxf(m, x);
+            mask |= (x > st.thr) ? (1u << i) : 0u;
         }
-        if (m > st.thr) {
+        if (mask) {
+            // rare per lane (a few % of lanes per chunk): spill the 32 keys so that the set bits
+            // can be walked with a dynamic index
+            float sp[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                if (f[i] > st.thr) {
-                    myk[st.cnt] = f[i];
-                    myi[st.cnt] = id0 + c0 + i;
-                    st.cnt++;
-                }
-            }
+            for (int i = 0; i < 32; i++) sp[i] = f[i];
+            do {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1;
+                myk[st.cnt] = sp[i];
+                myi[st.cnt] = id0 + c0 + i;
+                st.cnt++;
+            } while (mask);
         }
         unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
         while (need) {
