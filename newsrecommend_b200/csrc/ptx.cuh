@@ -83,6 +83,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without the release fence (which drains every outstanding global store of the thread,
+// MEMBAR.ALL.GPU): enough to hand a TMEM accumulator back, because the tcgen05.ld reads were
+// already completed by tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {

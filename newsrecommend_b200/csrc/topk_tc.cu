@@ -10,9 +10,10 @@
 //                     of 32 fp32 (128-byte swizzled rows), mbarrier ring
 //   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
 //                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
-//   warps 2-5, 6-9    two epilogue warpgroups; warpgroup g owns TMEM accumulator g, i.e. every
-//                     second tile: tcgen05.ld the 128 x 256 accumulator (one query row per
-//                     thread), turn scores into keys, append everything above the row's running
+//   warps 2-17        four epilogue warpgroups; warpgroup g works on TMEM accumulator g&1 (every
+//                     second tile) and column half g>>1 of it: tcgen05.ld 128 x 128 scores (one
+//                     query row per thread), turn scores into keys, append everything above the
+//                     row's running
 //                     threshold to the row's candidate buffer; a warp-cooperative bitonic
 //                     prune brings a full buffer back to the best k and raises the threshold.
 //                     Each warpgroup keeps its own per-row state and writes its own partial
@@ -45,8 +46,9 @@ constexpr int KC = 32;    // fp32 elements per K chunk (128-byte swizzle span)
 constexpr int A_BYTES = BM * KC * 4;        // 16 KB: 128 rows x 128 B
 constexpr int BH_BYTES = (BN / 2) * KC * 4; // 16 KB: half item tile (v2)
 constexpr int B_BYTES = BN * KC * 4;        // 32 KB: full item tile (v1)
-constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups of 4 warps
-constexpr int EPI_WGS = 2;
+constexpr int EPI_WGS = 4;  // epilogue warpgroups: (accumulator 0/1) x (column half 0/1)
+constexpr int NUM_THREADS = 64 + EPI_WGS * 128;  // TMA warp, MMA warp, 4 warps per epilogue warpgroup
+constexpr int HALF_N = BN / 2;
 constexpr int TMEM_COLS = 512;
 
 constexpr int V1_STAGES = 2;
@@ -62,7 +64,7 @@ struct TcShared {
     uint64_t tempty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[2][2][BN];  // [warpgroup][its own tile parity]: staged item norms (L2)
+    float nrm[EPI_WGS][2][HALF_N];  // [warpgroup][its own tile parity]: staged item norms (L2)
 };
 
 constexpr size_t V1_SMEM = (size_t)V1_STAGES * V1_STAGE_BYTES + sizeof(TcShared<V1_STAGES>) + 1024;
@@ -89,7 +91,7 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
                                          float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                          int lane) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < HALF_N; c0 += 32) {  // taddr0 / id0 / nrm / valid are relative to the column half
         if (!FULL && c0 >= valid) break;  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
@@ -170,15 +172,11 @@ template <bool L2>
 __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
                                                 int valid, int64_t b_total, int etid, int wg) {
     if (L2) {
-        // stage the tile's item norms; the warpgroup's named barrier also orders reuse of the buffer
-        for (int c = etid; c < BN; c += 128) {
-            const int64_t br = (int64_t)un.b_row0 + col_base + c;
-            nrm[c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
-        }
-        if (wg == 0)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        else
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+        // stage the norms of this warpgroup's 128 columns (one per thread); the warpgroup's named
+        // barrier also orders reuse of the buffer
+        const int64_t br = (int64_t)un.b_row0 + col_base + etid;
+        nrm[etid] = (etid < valid && br < b_total) ? b_norms[br] : 0.f;
+        asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
     }
 }
 
@@ -208,9 +206,11 @@ struct EpiArgs {
 
 template <bool L2, bool PAIR, bool NEED_QN>
 __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
-                                             float (*nrm)[2][BN], uint32_t tmem_base, int warp, int lane,
+                                             float (*nrm)[2][HALF_N], uint32_t tmem_base, int warp, int lane,
                                              uint32_t rank) {
-    const int wg = (warp - 2) >> 2;
+    const int wg = (warp - 2) >> 2;    // 0..3
+    const int acc = wg & 1;            // TMEM accumulator this warpgroup reads
+    const int half = wg >> 1;          // its column half of that accumulator
     const int quad = warp & 3;         // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;  // query row inside the tile
     const int etid = ((warp - 2) & 3) * 32 + lane;
@@ -219,14 +219,11 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
     int* ci = A.cand_idx_buf + crow0 * CAND_CAP;
     float* myk = ck + (int64_t)lane * CAND_CAP;
     int* myi = ci + (int64_t)lane * CAND_CAP;
-    uint32_t tempty_remote[2] = {0, 0};
-    if (PAIR) {
-        tempty_remote[0] = ptx::mapa_u32(&tempty[0], 0);
-        tempty_remote[1] = ptx::mapa_u32(&tempty[1], 0);
-    }
+    const uint32_t tempty_remote = PAIR ? ptx::mapa_u32(&tempty[acc], 0) : 0;
     const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int count = PAIR ? (A.n_units + 1) >> 1 : A.n_units;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
     uint32_t gt = 0;  // running tile index of this CTA (same sequence as the MMA warp)
     for (int i = first; i < count; i += stride) {
         const int u = PAIR ? 2 * i + (int)rank : i;
@@ -243,32 +240,31 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         st.gslot = nullptr;
         if (A.gthr && live) st.gslot = A.gthr + (A.row_map ? A.row_map[ar] / A.row_div : (int)ar);
         for (int t = 0; t < ntiles; t++, gt++) {
-            if ((int)(gt & 1) != wg) continue;  // the other warpgroup's accumulator
-            if (st.gslot) {  // pick up what the query's other units have established so far
-                const float g = from_ordered_u32(*(volatile unsigned*)st.gslot);
-                st.thr = fmaxf(st.thr, g - st.margin);
-            }
-            const int acc = wg;
+            if ((int)(gt & 1) != acc) continue;  // the other accumulator's warpgroups
             const uint32_t acc_phase = (gt >> 1) & 1;
-            const int col_base = t * BN;
-            const int valid = un.b_rows - col_base;
-            // two norm buffers per warpgroup: a fast warp may stage tile n+1 of this warpgroup
-            // while a slow one still reads tile n (the named barrier keeps them within one tile)
+            const int col_base = t * BN + half * HALF_N;  // first item column of this warpgroup's half
+            const int valid = un.b_rows - col_base;       // may be <= 0: nothing of this half is real
+            // issued before the wait so that its latency hides behind the MMAs: what the query's
+            // other units (lists, tail chunks, warpgroups) have established so far
+            unsigned g_raw = 0;
+            if (st.gslot) g_raw = *(volatile unsigned*)st.gslot;
+            // two norm buffers per warpgroup: a fast warp may stage its next tile while a slow
+            // one still reads the current one (the named barrier keeps them within one tile)
             float* nrm_t = nrm[wg][acc_phase];
             epi_stage_norms<L2>(nrm_t, A.b_norms, un, col_base, valid, A.b_total, etid, wg);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-            if (valid >= BN)
+            if (st.gslot) st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
+            if (valid >= HALF_N)
                 epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            else
+            else if (valid > 0)
                 epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            // accumulator drained: hand it back to the MMA warp
+            // this warp's part of the accumulator is drained: hand it back to the MMA warp
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (PAIR)
-                    ptx::mbar_arrive_cluster(tempty_remote[acc]);
+                    ptx::mbar_arrive_cluster_relaxed(tempty_remote);
                 else
                     ptx::mbar_arrive(&tempty[acc]);
             }
@@ -305,7 +301,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 4);
+            ptx::mbar_init(&sh->tempty[a], 8);  // 2 warpgroups x 4 warps read each accumulator
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
@@ -437,7 +433,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);   // multicast tcgen05.commit from the leader
-            ptx::mbar_init(&sh->tempty[a], 8);  // leader: 4 epilogue warps of each CTA
+            ptx::mbar_init(&sh->tempty[a], 16);  // leader: 2 warpgroups x 4 warps of each CTA
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
@@ -566,7 +562,7 @@ struct Tc3Shared {
     uint64_t aempty;
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[2][2][BN];
+    float nrm[EPI_WGS][2][HALF_N];
 };
 constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared) + 1024;
 
@@ -596,7 +592,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 8);
+            ptx::mbar_init(&sh->tempty[a], 16);
         }
         ptx::mbar_init(&sh->afull, 1);
         ptx::mbar_init(&sh->aempty, 1);
