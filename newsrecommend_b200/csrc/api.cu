@@ -82,7 +82,7 @@ struct FlatPlan {
     int tsplit;      // s (>= 1)
     int chunk_rows;  // item rows per tail chunk (multiple of 256)
     int n_units;     // 2 * (R + T * s)
-    int wgs;         // epilogue warpgroups writing partial rows (4 for the tcgen05 kernels)
+    int wgs;         // epilogue warpgroups writing partial rows (2 for the tcgen05 kernels)
     int S;           // source slots per query = tsplit * wgs
     int grid;
 };
@@ -91,7 +91,7 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     (void)k;
     FlatPlan p;
     const bool simt = path == NRB_PATH_SIMT;
-    p.wgs = simt ? 1 : 4;  // partial rows per unit row: the tcgen05 kernels run 4 epilogue warpgroups
+    p.wgs = simt ? 1 : 2;
     p.nqt = (int)((nq + UNIT_ROWS - 1) / UNIT_ROWS);
     if (p.nqt < 1) p.nqt = 1;
     p.npairs = (p.nqt + 1) / 2;
@@ -275,7 +275,7 @@ static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int
     if (p.maxsplit < 1) p.maxsplit = 1;
     int64_t mu = (p.npairs / UNIT_ROWS + 2 * (int64_t)nlist) * p.maxsplit;
     p.max_units = (int)mu;
-    p.wgs = path == NRB_PATH_SIMT ? 1 : 4;
+    p.wgs = path == NRB_PATH_SIMT ? 1 : 2;
     p.grid = path == NRB_PATH_SIMT ? simt_grid(p.max_units) : tc_grid(p.max_units);
     return p;
 }

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+
 // Same without the release fence (which drains every outstanding global store of the thread,
 // MEMBAR.ALL.GPU): enough to hand a TMEM accumulator back, because the tcgen05.ld reads were
 // already completed by tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync.
@@ -216,6 +217,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;     // SBO: 8 rows * 128 B
     d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+
+// The same descriptor split in two 32-bit halves: the high word is a compile-time constant, the
+// low word is (addr >> 4) | LBO, so stepping through K costs one add in the issuing loop.
+constexpr uint32_t UMMA_DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+    return ((smem_addr >> 4) & 0x3FFF) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(UMMA_DESC_HI_SW128));
     return d;
 }
 

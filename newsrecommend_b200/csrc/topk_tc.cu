@@ -10,10 +10,9 @@
 //                     of 32 fp32 (128-byte swizzled rows), mbarrier ring
 //   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
 //                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
-//   warps 2-17        four epilogue warpgroups; warpgroup g works on TMEM accumulator g&1 (every
-//                     second tile) and column half g>>1 of it: tcgen05.ld 128 x 128 scores (one
-//                     query row per thread), turn scores into keys, append everything above the
-//                     row's running
+//   warps 2-5, 6-9    two epilogue warpgroups; warpgroup g owns TMEM accumulator g, i.e. every
+//                     second tile: tcgen05.ld the 128 x 256 accumulator (one query row per
+//                     thread), turn scores into keys, append everything above the row's running
 //                     threshold to the row's candidate buffer; a warp-cooperative bitonic
 //                     prune brings a full buffer back to the best k and raises the threshold.
 //                     Each warpgroup keeps its own per-row state and writes its own partial
@@ -46,9 +45,8 @@ constexpr int KC = 32;    // fp32 elements per K chunk (128-byte swizzle span)
 constexpr int A_BYTES = BM * KC * 4;        // 16 KB: 128 rows x 128 B
 constexpr int BH_BYTES = (BN / 2) * KC * 4; // 16 KB: half item tile (v2)
 constexpr int B_BYTES = BN * KC * 4;        // 32 KB: full item tile (v1)
-constexpr int EPI_WGS = 4;  // epilogue warpgroups: (accumulator 0/1) x (column half 0/1)
-constexpr int NUM_THREADS = 64 + EPI_WGS * 128;  // TMA warp, MMA warp, 4 warps per epilogue warpgroup
-constexpr int HALF_N = BN / 2;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups of 4 warps
+constexpr int EPI_WGS = 2;
 constexpr int TMEM_COLS = 512;
 
 constexpr int V1_STAGES = 2;
@@ -64,7 +62,7 @@ struct TcShared {
     uint64_t tempty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[EPI_WGS][2][HALF_N];  // [warpgroup][its own tile parity]: staged item norms (L2)
+    float nrm[2][2][BN];  // [warpgroup][its own tile parity]: staged item norms (L2)
 };
 
 constexpr size_t V1_SMEM = (size_t)V1_STAGES * V1_STAGE_BYTES + sizeof(TcShared<V1_STAGES>) + 1024;
@@ -91,7 +89,7 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
                                          float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                          int lane) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < HALF_N; c0 += 32) {  // taddr0 / id0 / nrm / valid are relative to the column half
+    for (int c0 = 0; c0 < BN; c0 += 32) {
         if (!FULL && c0 >= valid) break;  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
@@ -172,11 +170,15 @@ template <bool L2>
 __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
                                                 int valid, int64_t b_total, int etid, int wg) {
     if (L2) {
-        // stage the norms of this warpgroup's 128 columns (one per thread); the warpgroup's named
-        // barrier also orders reuse of the buffer
-        const int64_t br = (int64_t)un.b_row0 + col_base + etid;
-        nrm[etid] = (etid < valid && br < b_total) ? b_norms[br] : 0.f;
-        asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+        // stage the tile's item norms; the warpgroup's named barrier also orders reuse of the buffer
+        for (int c = etid; c < BN; c += 128) {
+            const int64_t br = (int64_t)un.b_row0 + col_base + c;
+            nrm[c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
+        }
+        if (wg == 0)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        else
+            asm volatile("bar.sync 2, 128;" ::: "memory");
     }
 }
 
@@ -206,11 +208,9 @@ struct EpiArgs {
 
 template <bool L2, bool PAIR, bool NEED_QN>
 __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
-                                             float (*nrm)[2][HALF_N], uint32_t tmem_base, int warp, int lane,
+                                             float (*nrm)[2][BN], uint32_t tmem_base, int warp, int lane,
                                              uint32_t rank) {
-    const int wg = (warp - 2) >> 2;    // 0..3
-    const int acc = wg & 1;            // TMEM accumulator this warpgroup reads
-    const int half = wg >> 1;          // its column half of that accumulator
+    const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;         // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;  // query row inside the tile
     const int etid = ((warp - 2) & 3) * 32 + lane;
@@ -219,11 +219,14 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
     int* ci = A.cand_idx_buf + crow0 * CAND_CAP;
     float* myk = ck + (int64_t)lane * CAND_CAP;
     int* myi = ci + (int64_t)lane * CAND_CAP;
-    const uint32_t tempty_remote = PAIR ? ptx::mapa_u32(&tempty[acc], 0) : 0;
+    uint32_t tempty_remote[2] = {0, 0};
+    if (PAIR) {
+        tempty_remote[0] = ptx::mapa_u32(&tempty[0], 0);
+        tempty_remote[1] = ptx::mapa_u32(&tempty[1], 0);
+    }
     const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int count = PAIR ? (A.n_units + 1) >> 1 : A.n_units;
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
     uint32_t gt = 0;  // running tile index of this CTA (same sequence as the MMA warp)
     for (int i = first; i < count; i += stride) {
         const int u = PAIR ? 2 * i + (int)rank : i;
@@ -240,31 +243,33 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         st.gslot = nullptr;
         if (A.gthr && live) st.gslot = A.gthr + (A.row_map ? A.row_map[ar] / A.row_div : (int)ar);
         for (int t = 0; t < ntiles; t++, gt++) {
-            if ((int)(gt & 1) != acc) continue;  // the other accumulator's warpgroups
-            const uint32_t acc_phase = (gt >> 1) & 1;
-            const int col_base = t * BN + half * HALF_N;  // first item column of this warpgroup's half
-            const int valid = un.b_rows - col_base;       // may be <= 0: nothing of this half is real
+            if ((int)(gt & 1) != wg) continue;  // the other warpgroup's accumulator
             // issued before the wait so that its latency hides behind the MMAs: what the query's
-            // other units (lists, tail chunks, warpgroups) have established so far
+            // other units (lists, tail chunks, the other warpgroup) have established so far
             unsigned g_raw = 0;
             if (st.gslot) g_raw = *(volatile unsigned*)st.gslot;
-            // two norm buffers per warpgroup: a fast warp may stage its next tile while a slow
-            // one still reads the current one (the named barrier keeps them within one tile)
+            const int acc = wg;
+            const uint32_t acc_phase = (gt >> 1) & 1;
+            const int col_base = t * BN;
+            const int valid = un.b_rows - col_base;
+            // two norm buffers per warpgroup: a fast warp may stage tile n+1 of this warpgroup
+            // while a slow one still reads tile n (the named barrier keeps them within one tile)
             float* nrm_t = nrm[wg][acc_phase];
             epi_stage_norms<L2>(nrm_t, A.b_norms, un, col_base, valid, A.b_total, etid, wg);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
             if (st.gslot) st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
-            if (valid >= HALF_N)
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+            if (valid >= BN)
                 epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            else if (valid > 0)
+            else
                 epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            // this warp's part of the accumulator is drained: hand it back to the MMA warp
+            // accumulator drained: hand it back to the MMA warp
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (PAIR)
-                    ptx::mbar_arrive_cluster_relaxed(tempty_remote);
+                    ptx::mbar_arrive_cluster_relaxed(tempty_remote[acc]);
                 else
                     ptx::mbar_arrive(&tempty[acc]);
             }
@@ -301,7 +306,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 8);  // 2 warpgroups x 4 warps read each accumulator
+            ptx::mbar_init(&sh->tempty[a], 4);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
@@ -318,74 +323,80 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
 
+    // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow), and
+    // only the instruction with side effects is issued by one elected lane: issued from divergent
+    // code, every UTMALDG / UTCHMMA gets wrapped by ptxas in a waterfall loop that moves its
+    // operands to uniform registers one by one, which made the MMA-issuing thread the bottleneck.
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const Unit un = units[u];
-                const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
-                for (int t = 0; t < ntiles; t++) {
-                    const int brow = un.b_row0 + t * BN;
-                    for (int kc = 0; kc < nkc; kc++) {
-                        ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
-                        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const Unit un = units[u];
+            const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int brow = un.b_row0 + t * BN;
+                for (int kc = 0; kc < nkc; kc++) {
+                    ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+                    if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&sh->full[stage], STAGE_BYTES);
                         ptx::tma_load_2d(st, &map_ah, &sh->full[stage], kc * KC, un.a_row0);
                         ptx::tma_load_2d(st + A_BYTES, &map_al, &sh->full[stage], kc * KC, un.a_row0);
                         ptx::tma_load_2d(st + 2 * A_BYTES, &map_bh, &sh->full[stage], kc * KC, brow);
                         ptx::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_bl, &sh->full[stage], kc * KC, brow);
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_tf32(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const Unit un = units[u];
-                const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
-                for (int t = 0; t < ntiles; t++) {
-                    ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
+        constexpr uint32_t idesc = ptx::umma_idesc_tf32(BM, BN);
+        const uint32_t lo0 = ptx::umma_desc_lo(ptx::smem_u32(smem));
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const Unit un = units[u];
+            const int ntiles = un.a_rows > 0 ? (un.b_rows + BN - 1) / BN : 0;
+            for (int t = 0; t < ntiles; t++) {
+                ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
+                ptx::tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < nkc; kc++) {
+                    ptx::mbar_wait(&sh->full[stage], phase);
                     ptx::tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kc = 0; kc < nkc; kc++) {
-                        ptx::mbar_wait(&sh->full[stage], phase);
-                        ptx::tcgen05_fence_after();
-                        const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                        const uint32_t s_ah = sa, s_al = sa + A_BYTES, s_bh = sa + 2 * A_BYTES,
-                                       s_bl = sa + 2 * A_BYTES + B_BYTES;
+                    // descriptor low words advance by bytes/16: stage base, then 32 B per K step
+                    const uint32_t l_ah = lo0 + (uint32_t)(stage * STAGE_BYTES) / 16;
+                    const uint32_t l_al = l_ah + A_BYTES / 16, l_bh = l_ah + 2 * A_BYTES / 16,
+                                   l_bl = l_ah + (2 * A_BYTES + B_BYTES) / 16;
+                    if (ptx::elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < KC / 8; ks++) {
-                            const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes inside the swizzled row
-                            const uint64_t d_ah = ptx::umma_desc_sw128(s_ah + off);
-                            const uint64_t d_al = ptx::umma_desc_sw128(s_al + off);
-                            const uint64_t d_bh = ptx::umma_desc_sw128(s_bh + off);
-                            const uint64_t d_bl = ptx::umma_desc_sw128(s_bl + off);
+                            const uint64_t d_ah = ptx::umma_desc_join(l_ah + 2 * ks), d_al = ptx::umma_desc_join(l_al + 2 * ks);
+                            const uint64_t d_bh = ptx::umma_desc_join(l_bh + 2 * ks), d_bl = ptx::umma_desc_join(l_bl + 2 * ks);
                             ptx::umma_tf32(d_tmem, d_al, d_bh, idesc, (kc | ks) != 0);
                             ptx::umma_tf32(d_tmem, d_ah, d_bl, idesc, 1);
                             ptx::umma_tf32(d_tmem, d_ah, d_bh, idesc, 1);
                         }
                         ptx::umma_commit(&sh->empty[stage]);  // frees the smem stage when the MMAs retire
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
                     }
-                    ptx::umma_commit(&sh->tfull[acc]);  // accumulator complete
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+                if (ptx::elect_one()) ptx::umma_commit(&sh->tfull[acc]);  // accumulator complete
+                __syncwarp();
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
         }
     } else {
@@ -433,7 +444,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);   // multicast tcgen05.commit from the leader
-            ptx::mbar_init(&sh->tempty[a], 16);  // leader: 2 warpgroups x 4 warps of each CTA
+            ptx::mbar_init(&sh->tempty[a], 8);  // leader: 4 epilogue warps of each CTA
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
@@ -453,36 +464,38 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            uint32_t full0[STAGES];  // the leader's full barriers (shared::cluster addresses)
-            for (int s = 0; s < STAGES; s++) full0[s] = ptx::mapa_u32(&sh->full[s], 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
-                const Unit un = units[2 * p + rank];
-                const int ntiles = (un.b_rows + BN - 1) / BN;
-                for (int t = 0; t < ntiles; t++) {
-                    const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);  // this CTA's half of the item tile
-                    for (int kc = 0; kc < nkc; kc++) {
-                        ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
-                        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+        const uint32_t full0_base = ptx::mapa_u32(&sh->full[0], 0);  // the leader's full barriers
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+            const Unit un = units[2 * p + rank];
+            const int ntiles = (un.b_rows + BN - 1) / BN;
+            for (int t = 0; t < ntiles; t++) {
+                const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);  // this CTA's half of the item tile
+                for (int kc = 0; kc < nkc; kc++) {
+                    ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+                    const uint32_t fb = full0_base + (uint32_t)stage * 8;
+                    if (ptx::elect_one()) {
                         if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * STAGE_BYTES);
-                        ptx::tma_load_2d_cg2(st, &map_ah, full0[stage], kc * KC, un.a_row0);
-                        ptx::tma_load_2d_cg2(st + A_BYTES, &map_al, full0[stage], kc * KC, un.a_row0);
-                        ptx::tma_load_2d_cg2(st + 2 * A_BYTES, &map_bh, full0[stage], kc * KC, brow);
-                        ptx::tma_load_2d_cg2(st + 2 * A_BYTES + BH_BYTES, &map_bl, full0[stage], kc * KC, brow);
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        ptx::tma_load_2d_cg2(st, &map_ah, fb, kc * KC, un.a_row0);
+                        ptx::tma_load_2d_cg2(st + A_BYTES, &map_al, fb, kc * KC, un.a_row0);
+                        ptx::tma_load_2d_cg2(st + 2 * A_BYTES, &map_bh, fb, kc * KC, brow);
+                        ptx::tma_load_2d_cg2(st + 2 * A_BYTES + BH_BYTES, &map_bl, fb, kc * KC, brow);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * BM, BN);
+            const uint32_t lo0 = ptx::umma_desc_lo(ptx::smem_u32(smem));
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -497,27 +510,28 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                     for (int kc = 0; kc < nkc; kc++) {
                         ptx::mbar_wait(&sh->full[stage], phase);
                         ptx::tcgen05_fence_after();
-                        const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                        const uint32_t s_ah = sa, s_al = sa + A_BYTES, s_bh = sa + 2 * A_BYTES,
-                                       s_bl = sa + 2 * A_BYTES + BH_BYTES;
+                        const uint32_t l_ah = lo0 + (uint32_t)(stage * STAGE_BYTES) / 16;
+                        const uint32_t l_al = l_ah + A_BYTES / 16, l_bh = l_ah + 2 * A_BYTES / 16,
+                                       l_bl = l_ah + (2 * A_BYTES + BH_BYTES) / 16;
+                        if (ptx::elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < KC / 8; ks++) {
-                            const uint32_t off = ks * 32;
-                            const uint64_t d_ah = ptx::umma_desc_sw128(s_ah + off);
-                            const uint64_t d_al = ptx::umma_desc_sw128(s_al + off);
-                            const uint64_t d_bh = ptx::umma_desc_sw128(s_bh + off);
-                            const uint64_t d_bl = ptx::umma_desc_sw128(s_bl + off);
-                            ptx::umma_tf32_cg2(d_tmem, d_al, d_bh, idesc, (kc | ks) != 0);
-                            ptx::umma_tf32_cg2(d_tmem, d_ah, d_bl, idesc, 1);
-                            ptx::umma_tf32_cg2(d_tmem, d_ah, d_bh, idesc, 1);
+                            for (int ks = 0; ks < KC / 8; ks++) {
+                                const uint64_t d_ah = ptx::umma_desc_join(l_ah + 2 * ks), d_al = ptx::umma_desc_join(l_al + 2 * ks);
+                                const uint64_t d_bh = ptx::umma_desc_join(l_bh + 2 * ks), d_bl = ptx::umma_desc_join(l_bl + 2 * ks);
+                                ptx::umma_tf32_cg2(d_tmem, d_al, d_bh, idesc, (kc | ks) != 0);
+                                ptx::umma_tf32_cg2(d_tmem, d_ah, d_bl, idesc, 1);
+                                ptx::umma_tf32_cg2(d_tmem, d_ah, d_bh, idesc, 1);
+                            }
+                            ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);  // both CTAs' stage is free
                         }
-                        ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);  // both CTAs' stage is free
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);  // both CTAs' accumulator halves complete
+                    if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);  // both halves complete
+                    __syncwarp();
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -562,7 +576,7 @@ struct Tc3Shared {
     uint64_t aempty;
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[EPI_WGS][2][HALF_N];
+    float nrm[2][2][BN];
 };
 constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared) + 1024;
 
@@ -592,7 +606,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 16);
+            ptx::mbar_init(&sh->tempty[a], 8);
         }
         ptx::mbar_init(&sh->afull, 1);
         ptx::mbar_init(&sh->aempty, 1);
@@ -612,40 +626,45 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            uint32_t full0[STAGES];
-            for (int s = 0; s < STAGES; s++) full0[s] = ptx::mapa_u32(&sh->full[s], 0);
-            const uint32_t afull0 = ptx::mapa_u32(&sh->afull, 0);
-            int stage = 0;
-            uint32_t phase = 0, a_phase = 0;
-            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
-                const Unit un = units[2 * p + rank];
-                const int ntiles = (un.b_rows + BN - 1) / BN;
-                // the unit's query tile, once
-                ptx::mbar_wait(&sh->aempty, a_phase ^ 1);
+        const uint32_t full0_base = ptx::mapa_u32(&sh->full[0], 0);
+        const uint32_t afull0 = ptx::mapa_u32(&sh->afull, 0);
+        int stage = 0;
+        uint32_t phase = 0, a_phase = 0;
+        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
+            const Unit un = units[2 * p + rank];
+            const int ntiles = (un.b_rows + BN - 1) / BN;
+            // the unit's query tile, once
+            ptx::mbar_wait(&sh->aempty, a_phase ^ 1);
+            if (ptx::elect_one()) {
                 if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
                 for (int kc = 0; kc < nkc; kc++)
                     ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KC, un.a_row0);
-                a_phase ^= 1;
-                for (int t = 0; t < ntiles; t++) {
-                    const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);
-                    for (int kc = 0; kc < nkc; kc++) {
-                        ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+            }
+            __syncwarp();
+            a_phase ^= 1;
+            for (int t = 0; t < ntiles; t++) {
+                const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);
+                for (int kc = 0; kc < nkc; kc++) {
+                    ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                    const uint32_t fb = full0_base + (uint32_t)stage * 8;
+                    if (ptx::elect_one()) {
                         if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * BH_BYTES);
-                        ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BH_BYTES, &map_bh, full0[stage], kc * KC, brow);
-                        if (++stage == STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BH_BYTES, &map_bh, fb, kc * KC, brow);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * BM, BN);
-            const uint32_t sa0 = ptx::smem_u32(smem);
+            const uint32_t la0 = ptx::umma_desc_lo(ptx::smem_u32(smem));
+            const uint32_t lb0 = ptx::umma_desc_lo(ptx::smem_u32(smem_b));
             int stage = 0;
             uint32_t phase = 0, a_phase = 0;
             int acc = 0;
@@ -663,25 +682,29 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                     for (int kc = 0; kc < nkc; kc++) {
                         ptx::mbar_wait(&sh->full[stage], phase);
                         ptx::tcgen05_fence_after();
-                        const uint32_t s_a = sa0 + (uint32_t)kc * A_BYTES;
-                        const uint32_t s_b = ptx::smem_u32(smem_b + (size_t)stage * BH_BYTES);
+                        const uint32_t l_a = la0 + (uint32_t)(kc * A_BYTES) / 16;
+                        const uint32_t l_b = lb0 + (uint32_t)(stage * BH_BYTES) / 16;
+                        if (ptx::elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < KC / 8; ks++) {
-                            const uint32_t off = ks * 32;
-                            ptx::umma_tf32_cg2(d_tmem, ptx::umma_desc_sw128(s_a + off), ptx::umma_desc_sw128(s_b + off),
-                                               idesc, (kc | ks) != 0);
+                            for (int ks = 0; ks < KC / 8; ks++)
+                                ptx::umma_tf32_cg2(d_tmem, ptx::umma_desc_join(l_a + 2 * ks),
+                                                   ptx::umma_desc_join(l_b + 2 * ks), idesc, (kc | ks) != 0);
+                            ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);
                         }
-                        ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);
+                    if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);
+                    __syncwarp();
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
-                ptx::umma_commit_cg2_mc(&sh->aempty, 3);  // query tile may be replaced once these MMAs retire
+                // query tile may be replaced once these MMAs retire
+                if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&sh->aempty, 3);
+                __syncwarp();
             }
         }
     } else {
