@@ -51,11 +51,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (error at the next sync) instead of hanging the GPU.
+// SLEEP_NS > 0 backs off between polls: for waits with slack (the TMA producer has several
+// stages of lead) so that the spinning warp does not take issue slots from the warps that
+// share its scheduler.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if (++spins > (SLEEP_NS > 0 ? 20000000u : 400000000u)) {  // seconds: far beyond any legitimate wait
             printf("nrb200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
             __trap();

@@ -10,9 +10,10 @@
 //                     of 32 fp32 (128-byte swizzled rows), mbarrier ring
 //   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
 //                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
-//   warps 2-5, 6-9    two epilogue warpgroups; warpgroup g owns TMEM accumulator g, i.e. every
-//                     second tile: tcgen05.ld the 128 x 256 accumulator (one query row per
-//                     thread), turn scores into keys, append everything above the row's running
+//   warps 2-5, 6-9    two epilogue warpgroups; warpgroup g takes columns [128g, 128g+128) of EVERY
+//                     tile (so the epilogue runs back to back while the other accumulator's
+//                     MMAs execute): tcgen05.ld 128 x 128 scores (one query row per thread),
+//                     turn scores into keys, append everything above the row's running
 //                     threshold to the row's candidate buffer; a warp-cooperative bitonic
 //                     prune brings a full buffer back to the best k and raises the threshold.
 //                     Each warpgroup keeps its own per-row state and writes its own partial
@@ -47,6 +48,7 @@ constexpr int BH_BYTES = (BN / 2) * KC * 4; // 16 KB: half item tile (v2)
 constexpr int B_BYTES = BN * KC * 4;        // 32 KB: full item tile (v1)
 constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups of 4 warps
 constexpr int EPI_WGS = 2;
+constexpr int HALF_N = BN / EPI_WGS;  // columns of every tile handled by one warpgroup
 constexpr int TMEM_COLS = 512;
 
 constexpr int V1_STAGES = 2;
@@ -62,7 +64,7 @@ struct TcShared {
     uint64_t tempty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[2][2][BN];  // [warpgroup][its own tile parity]: staged item norms (L2)
+    float nrm[EPI_WGS][2][HALF_N];  // [warpgroup][tile parity]: staged item norms (L2)
 };
 
 constexpr size_t V1_SMEM = (size_t)V1_STAGES * V1_STAGE_BYTES + sizeof(TcShared<V1_STAGES>) + 1024;
@@ -89,7 +91,7 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
                                          float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                          int lane) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < HALF_N; c0 += 32) {  // taddr0 / id0 / nrm / valid are relative to the warpgroup's columns
         if (!FULL && c0 >= valid) break;  // warp-uniform
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
@@ -170,11 +172,10 @@ template <bool L2>
 __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
                                                 int valid, int64_t b_total, int etid, int wg) {
     if (L2) {
-        // stage the tile's item norms; the warpgroup's named barrier also orders reuse of the buffer
-        for (int c = etid; c < BN; c += 128) {
-            const int64_t br = (int64_t)un.b_row0 + col_base + c;
-            nrm[c] = (c < valid && br < b_total) ? b_norms[br] : 0.f;
-        }
+        // stage the norms of this warpgroup's 128 columns (one per thread); the warpgroup's named
+        // barrier also orders reuse of the buffer
+        const int64_t br = (int64_t)un.b_row0 + col_base + etid;
+        nrm[etid] = (etid < valid && br < b_total) ? b_norms[br] : 0.f;
         if (wg == 0)
             asm volatile("bar.sync 1, 128;" ::: "memory");
         else
@@ -208,9 +209,9 @@ struct EpiArgs {
 
 template <bool L2, bool PAIR, bool NEED_QN>
 __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
-                                             float (*nrm)[2][BN], uint32_t tmem_base, int warp, int lane,
+                                             float (*nrm)[2][HALF_N], uint32_t tmem_base, int warp, int lane,
                                              uint32_t rank) {
-    const int wg = (warp - 2) >> 2;
+    const int wg = (warp - 2) >> 2;    // warpgroup = column half of every tile
     const int quad = warp & 3;         // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;  // query row inside the tile
     const int etid = ((warp - 2) & 3) * 32 + lane;
@@ -227,6 +228,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
     const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int count = PAIR ? (A.n_units + 1) >> 1 : A.n_units;
+    const uint32_t taddr_wg = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(wg * HALF_N);
     uint32_t gt = 0;  // running tile index of this CTA (same sequence as the MMA warp)
     for (int i = first; i < count; i += stride) {
         const int u = PAIR ? 2 * i + (int)rank : i;
@@ -243,28 +245,27 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         st.gslot = nullptr;
         if (A.gthr && live) st.gslot = A.gthr + (A.row_map ? A.row_map[ar] / A.row_div : (int)ar);
         for (int t = 0; t < ntiles; t++, gt++) {
-            if ((int)(gt & 1) != wg) continue;  // the other warpgroup's accumulator
+            const int acc = (int)(gt & 1);
+            const uint32_t acc_phase = (gt >> 1) & 1;
+            const int col_base = t * BN + wg * HALF_N;  // first item column of this warpgroup's half
+            const int valid = un.b_rows - col_base;     // may be <= 0: nothing of this half is real
             // issued before the wait so that its latency hides behind the MMAs: what the query's
             // other units (lists, tail chunks, the other warpgroup) have established so far
             unsigned g_raw = 0;
             if (st.gslot) g_raw = *(volatile unsigned*)st.gslot;
-            const int acc = wg;
-            const uint32_t acc_phase = (gt >> 1) & 1;
-            const int col_base = t * BN;
-            const int valid = un.b_rows - col_base;
-            // two norm buffers per warpgroup: a fast warp may stage tile n+1 of this warpgroup
-            // while a slow one still reads tile n (the named barrier keeps them within one tile)
-            float* nrm_t = nrm[wg][acc_phase];
+            // two norm buffers per warpgroup: a fast warp may stage its next tile while a slow
+            // one still reads the current one (the named barrier keeps them within one tile)
+            float* nrm_t = nrm[wg][acc];
             epi_stage_norms<L2>(nrm_t, A.b_norms, un, col_base, valid, A.b_total, etid, wg);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
             if (st.gslot) st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-            if (valid >= BN)
+            const uint32_t taddr0 = taddr_wg + (uint32_t)(acc * BN);
+            if (valid >= HALF_N)
                 epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            else
+            else if (valid > 0)
                 epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            // accumulator drained: hand it back to the MMA warp
+            // this warp's part of the accumulator is drained: hand it back to the MMA warp
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -306,7 +307,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 4);
+            ptx::mbar_init(&sh->tempty[a], 8);  // both warpgroups (8 warps) read every accumulator
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
@@ -337,7 +338,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             for (int t = 0; t < ntiles; t++) {
                 const int brow = un.b_row0 + t * BN;
                 for (int kc = 0; kc < nkc; kc++) {
-                    ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                    ptx::mbar_wait<64>(&sh->empty[stage], phase ^ 1);
                     uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&sh->full[stage], STAGE_BYTES);
@@ -444,7 +445,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);   // multicast tcgen05.commit from the leader
-            ptx::mbar_init(&sh->tempty[a], 8);  // leader: 4 epilogue warps of each CTA
+            ptx::mbar_init(&sh->tempty[a], 16);  // leader: 8 epilogue warps of each CTA
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
@@ -473,7 +474,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             for (int t = 0; t < ntiles; t++) {
                 const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);  // this CTA's half of the item tile
                 for (int kc = 0; kc < nkc; kc++) {
-                    ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                    ptx::mbar_wait<64>(&sh->empty[stage], phase ^ 1);
                     uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
                     const uint32_t fb = full0_base + (uint32_t)stage * 8;
                     if (ptx::elect_one()) {
@@ -576,7 +577,7 @@ struct Tc3Shared {
     uint64_t aempty;
     uint32_t tmem_base;
     uint32_t pad;
-    float nrm[2][2][BN];
+    float nrm[EPI_WGS][2][HALF_N];
 };
 constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared) + 1024;
 
@@ -606,7 +607,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 8);
+            ptx::mbar_init(&sh->tempty[a], 16);
         }
         ptx::mbar_init(&sh->afull, 1);
         ptx::mbar_init(&sh->aempty, 1);
@@ -634,7 +635,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             const Unit un = units[2 * p + rank];
             const int ntiles = (un.b_rows + BN - 1) / BN;
             // the unit's query tile, once
-            ptx::mbar_wait(&sh->aempty, a_phase ^ 1);
+            ptx::mbar_wait<64>(&sh->aempty, a_phase ^ 1);
             if (ptx::elect_one()) {
                 if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
                 for (int kc = 0; kc < nkc; kc++)
@@ -645,7 +646,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             for (int t = 0; t < ntiles; t++) {
                 const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);
                 for (int kc = 0; kc < nkc; kc++) {
-                    ptx::mbar_wait(&sh->empty[stage], phase ^ 1);
+                    ptx::mbar_wait<64>(&sh->empty[stage], phase ^ 1);
                     const uint32_t fb = full0_base + (uint32_t)stage * 8;
                     if (ptx::elect_one()) {
                         if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * BH_BYTES);
