@@ -44,7 +44,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // key = -distance for L2. A candidate is the pair (key, idx); idx is a 32-bit row index
 // (>= 0). Candidates are ordered by (key descending, idx ascending), so exact ties resolve to
 // the lowest id the way faiss's k=1 strict-compare heap does.
-constexpr int CAND_CAP = 512;  // per-row candidate buffer capacity (entries)
+constexpr int CAND_CAP = 256;  // per-row candidate buffer capacity (entries)
 constexpr float NEG_INF = -__builtin_huge_valf();
 
 __device__ __forceinline__ uint64_t pack_cand(float key, int idx) {

@@ -123,33 +123,26 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
                 st.cnt++;
             } while (mask);
         }
-    }
-}
-
-// Brings every row of the warp whose buffer could overflow during the next tile (up to HALF_N
-// appends) back to its best k (+ margin set) and raises its threshold. Called once per tile
-// AFTER the accumulator was handed back, so that a prune (a 512-element bitonic sort) is off the
-// MMA <-> epilogue critical path: with 16 warps sharing every hand-off, a prune inside the tile
-// made nearly every tile wait for some straggler.
-__device__ __forceinline__ void epi_prune_full_rows(EpiRow& st, float* ck, int* ci, int k, int keep_max, int lane) {
-    unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - HALF_N);
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int n = __shfl_sync(0xffffffffu, st.cnt, src);
-        const float mg = __shfl_sync(0xffffffffu, st.margin, src);
-        const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
-        float* rk = ck + (int64_t)src * CAND_CAP;
-        int* ri = ci + (int64_t)src * CAND_CAP;
-        int kept;
-        bool ovf;
-        float kth;
-        const float tnew = warp_prune_row_m(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, lane, &kept, &ovf, fl, &kth);
-        if (lane == src) {
-            st.cnt = kept;
-            st.thr = tnew;
-            st.flag |= ovf ? 1 : 0;
-            if (st.gslot && kth > NEG_INF) atomicMax(st.gslot, ordered_u32(kth));
+        unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int n = __shfl_sync(0xffffffffu, st.cnt, src);
+            const float mg = __shfl_sync(0xffffffffu, st.margin, src);
+            const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
+            float* rk = ck + (int64_t)src * CAND_CAP;
+            int* ri = ci + (int64_t)src * CAND_CAP;
+            int kept;
+            bool ovf;
+            float kth;
+            const float tnew = warp_prune_row_m(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, lane, &kept, &ovf,
+                                                fl, &kth);
+            if (lane == src) {
+                st.cnt = kept;
+                st.thr = tnew;
+                st.flag |= ovf ? 1 : 0;
+                if (st.gslot && kth > NEG_INF) atomicMax(st.gslot, ordered_u32(kth));
+            }
         }
     }
 }
@@ -281,7 +274,6 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 else
                     ptx::mbar_arrive(&tempty[acc]);
             }
-            epi_prune_full_rows(st, ck, ci, A.k, A.pw, lane);
         }
         epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
                      A.part_idx, lane);
@@ -865,7 +857,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, cudaStream_t st) {
     NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", 128 - TC1_EXTRA);
-    NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - HALF_N, "tc1: bad kp / pw");
+    NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - 64, "tc1: bad kp / pw");
     NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
     if (scratch_bytes < tc_scratch_bytes(grid)) {
         set_error("tc1: scratch too small");
