@@ -142,6 +142,17 @@ int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* 
                    int32_t nprobe, int32_t metric, int32_t k, float* D, int64_t* I,
                    void* workspace, size_t workspace_bytes, int32_t path, void* stream);
 
+/* ---- neighbours of the path --------------------------------------------------- */
+/* Retrieval.py:33-34 batched: out[out_off[u] + j] = list_ids[list_off[user_list[u]] + j] for
+ * every member j of the user's nearest list (user_list[u] < 0: nothing). out_off is the
+ * exclusive prefix sum of the list lengths per user. */
+int nrb_expand_lists(const int64_t* user_list, const int32_t* list_off, const int64_t* list_ids,
+                     const int64_t* out_off, int64_t nu, int64_t* out, void* stream);
+/* utils.py:12-17 and finialize_retrieval.py:10-11: out[u] = 1 iff target[u] occurs in row u of
+ * the CSR (off i64[nrows+1], ids). */
+int nrb_csr_contains(const int64_t* off, const int64_t* ids, const int64_t* target, int64_t nrows,
+                     uint8_t* out, void* stream);
+
 /* ---- K4: k-way merge of per-shard results ------------------------------------------------- */
 /* Dp f32[nparts, nq, k], Ip i64[nparts, nq, k] (each best-first, -1 padded) -> global top-k.
  * Sits after the NCCL all-gather of the catalog-sharded search (north_star item 4). */

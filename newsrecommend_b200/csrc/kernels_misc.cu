@@ -777,3 +777,52 @@ extern "C" int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }
+
+// ------------------------------------------------------------------- candidate lists
+// Retrieval.py:33-34 batched: user u gets the whole inverted list of its nearest centroid.
+// Warp per user: out[out_off[u] + j] = list_ids[list_off[l_u] + j].
+__global__ void expand_lists_kernel(const int64_t* __restrict__ user_list, const int32_t* __restrict__ list_off,
+                                    const int64_t* __restrict__ list_ids, const int64_t* __restrict__ out_off,
+                                    int64_t nu, int64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= nu) return;
+    const int64_t l = user_list[u];
+    if (l < 0) return;
+    const int b = list_off[l], e = list_off[l + 1];
+    int64_t* dst = out + out_off[u];
+    for (int j = lane; j < e - b; j += 32) dst[j] = list_ids[b + j];
+}
+
+// utils.py:12-17 / finialize_retrieval.py:10-11: is target[u] in row u of the CSR (off, ids)?
+__global__ void csr_contains_kernel(const int64_t* __restrict__ off, const int64_t* __restrict__ ids,
+                                    const int64_t* __restrict__ target, int64_t nrows,
+                                    uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= nrows) return;
+    const int64_t t = target[u];
+    bool hit = false;
+    for (int64_t j = off[u] + lane; j < off[u + 1]; j += 32) hit |= (ids[j] == t);
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) out[u] = hit ? 1 : 0;
+}
+
+extern "C" int nrb_expand_lists(const int64_t* user_list, const int32_t* list_off, const int64_t* list_ids,
+                                const int64_t* out_off, int64_t nu, int64_t* out, void* stream) {
+    NRB_REQUIRE(nu >= 0, "expand_lists: bad size");
+    if (nu == 0) return NRB_OK;
+    expand_lists_kernel<<<(unsigned)((nu + 7) / 8), 256, 0, (cudaStream_t)stream>>>(user_list, list_off, list_ids,
+                                                                                   out_off, nu, out);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+extern "C" int nrb_csr_contains(const int64_t* off, const int64_t* ids, const int64_t* target, int64_t nrows,
+                                uint8_t* out, void* stream) {
+    NRB_REQUIRE(nrows >= 0, "csr_contains: bad size");
+    if (nrows == 0) return NRB_OK;
+    csr_contains_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(off, ids, target, nrows, out);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}

@@ -1,0 +1,88 @@
+"""GPU tests of the rows next to the hot path: the batched Retrieval.py stage, the
+finalize / hit-rate neighbours and the npy formats they exchange."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _synthetic_news(tmp_path, n=30000, nu=300, d=256):
+    from newsrecommend_b200 import synth
+    news = tmp_path / "news"
+    news.mkdir()
+    x, topics = synth.g_skew(n, d, 1, return_topics=True)
+    ids = np.arange(100000, 100000 + n, dtype=np.int64)
+    np.save(news / "article_table.npy", np.concatenate([x.astype(np.float64), ids[:, None].astype(np.float64)], axis=1))
+    users = synth.user_profiles(x, topics, nu, 2)
+    np.save(news / "test_user_profile.npy", {int(7 * u + 3): users[u] for u in range(nu)}, allow_pickle=True)
+    rng = np.random.default_rng(5)
+    gt = {int(7 * u + 3): int(ids[rng.integers(0, n)]) for u in range(nu)}
+    np.save(news / "test_user_ground_truth.npy", gt, allow_pickle=True)
+    return news, ids, x, users, gt
+
+
+def test_batched_stage_equals_reference_script(tmp_path):
+    """retrieve_candidates == the unmodified Retrieval.py run on the shim, user by user."""
+    from newsrecommend_b200 import pipeline
+    news, ids, x, users, gt = _synthetic_news(tmp_path)
+    aids, emb = pipeline.load_article_table(news / "article_table.npy")
+    assert np.array_equal(aids, ids) and emb.dtype == np.float32 and np.array_equal(emb, x)
+    uids, prof = pipeline.load_user_profiles(news / "test_user_profile.npy")
+    assert np.array_equal(prof, users)
+    out = pipeline.retrieve_candidates(aids, emb, prof, num_clusters=300, niter=80)
+    off, cand = out["offsets"].cpu().numpy(), out["candidates"].cpu().numpy()
+    assert off[-1] == cand.shape[0] and int(out["list_sizes"].sum()) == len(ids)
+    ref = "/root/reference/Retrieval.py"
+    if os.path.exists(ref):
+        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "shim") + os.pathsep + ROOT)
+        subprocess.check_call([sys.executable, ref], cwd=tmp_path, env=env)
+        u2, off2, cand2 = pipeline.load_recommendations(news / "test_user_recommendations.npy")
+        assert np.array_equal(u2, uids) and np.array_equal(off2, off) and np.array_equal(cand2, cand)
+    # structural checks that hold without the reference tree: a user's candidates are exactly
+    # the articles assigned to its nearest centroid, in ascending row order
+    assign = out["assignments"].cpu().numpy()
+    ul = out["user_list"].cpu().numpy()
+    for u in (0, 17, 299):
+        assert np.array_equal(cand[off[u]:off[u + 1]], ids[assign == ul[u]])
+    pipeline.save_recommendations(news / "rec2.npy", uids, off, cand)
+    u3, off3, cand3 = pipeline.load_recommendations(news / "rec2.npy")
+    assert np.array_equal(u3, uids) and np.array_equal(off3, off) and np.array_equal(cand3, cand)
+
+
+def test_finalize_and_hit_rate_match_the_scripts(tmp_path):
+    """finalize_candidates == finialize_retrieval.py:6-15 and hit_rate == utils.py:12-22, both
+    restated here in numpy exactly as the scripts compute them."""
+    from newsrecommend_b200 import pipeline
+    rng = np.random.default_rng(0)
+    nu = 500
+    lens = rng.integers(0, 40, size=nu)
+    off = np.zeros(nu + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    cand = rng.integers(0, 2000, size=off[-1]).astype(np.int64)
+    gt = rng.integers(0, 2000, size=nu).astype(np.int64)
+    for u in range(0, nu, 3):  # make a third of the users hits
+        if lens[u]:
+            gt[u] = cand[off[u] + rng.integers(0, lens[u])]
+    hits, hist = pipeline.hit_rate(off, cand, gt)
+    exp_hits = sum(int(gt[u] in cand[off[u]:off[u + 1]]) for u in range(nu))  # utils.py:14-16
+    assert hits == exp_hits
+    vals, counts = np.unique(lens, return_counts=True)
+    assert hist == dict(zip(vals.tolist(), counts.tolist()))               # utils.py:19-22
+    noff, ncand = pipeline.finalize_candidates(off, cand, gt)
+    noff, ncand = noff.cpu().numpy(), ncand.cpu().numpy()
+    for u in range(nu):                                                     # finialize_retrieval.py:10-13
+        rec = cand[off[u]:off[u + 1]]
+        exp = rec if gt[u] in rec else np.append(rec, gt[u])
+        assert np.array_equal(ncand[noff[u]:noff[u + 1]], exp)
+    assert pipeline.hit_rate(noff, ncand, gt)[0] == nu
+    # the intended cap (off by default): every list <= cap (+1 for the appended ground truth)
+    coff, ccand = pipeline.finalize_candidates(off, cand, gt, cap=10)
+    coff, ccand = coff.cpu().numpy(), ccand.cpu().numpy()
+    assert (np.diff(coff) <= 11).all()
+    for u in range(nu):
+        assert set(ccand[coff[u]:coff[u + 1]].tolist()) <= set(cand[off[u]:off[u + 1]].tolist()) | {int(gt[u])}
