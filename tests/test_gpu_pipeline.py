@@ -43,8 +43,29 @@ def test_batched_stage_equals_reference_script(tmp_path):
         subprocess.check_call([sys.executable, ref], cwd=tmp_path, env=env)
         u2, off2, cand2 = pipeline.load_recommendations(news / "test_user_recommendations.npy")
         assert np.array_equal(u2, uids) and np.array_equal(off2, off) and np.array_equal(cand2, cand)
-    # structural checks that hold without the reference tree: a user's candidates are exactly
-    # the articles assigned to its nearest centroid, in ascending row order
+    # The GPU box has no /root/reference, so the same call sequence the script makes
+    # (Retrieval.py:11-34) is replayed here against the shim, per-user loop included.
+    sys.path.insert(0, os.path.join(ROOT, "shim"))
+    try:
+        import faiss
+        clustering = faiss.Clustering(emb.shape[1], 300)                      # :12
+        clustering.niter = 80                                                 # :13
+        index = faiss.IndexHNSWFlat(emb.shape[1], 32)                         # :16
+        clustering.train(np.ascontiguousarray(emb), index)                    # :17-18
+        cents = faiss.vector_float_to_array(clustering.centroids).reshape(300, emb.shape[1])  # :19
+        _, a = index.search(emb, 1)                                           # :21
+        a = a.flatten()                                                       # :22
+        cluster_to_articles = {i: aids[a == i] for i in range(300)}           # :23
+        centroid_index = faiss.IndexFlatL2(emb.shape[1])                      # :25
+        centroid_index.add(cents)                                             # :26
+        for u in range(0, len(uids), 7):                                      # :30-34 (every 7th user)
+            _, I1 = centroid_index.search(prof[u].reshape(1, -1).astype(np.float32), 1)
+            assert np.array_equal(np.array(cluster_to_articles[int(I1[0, 0])]), cand[off[u]:off[u + 1]])
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("faiss", None)
+    # structural checks: a user's candidates are exactly the articles assigned to its nearest
+    # centroid, in ascending row order
     assign = out["assignments"].cpu().numpy()
     ul = out["user_list"].cpu().numpy()
     for u in (0, 17, 299):
