@@ -193,23 +193,49 @@ def run_ours(args):
     from newsrecommend_b200.sharded import ShardedIndexFlat
 
     xb, xq = make_data()
-    index = ShardedIndexFlat(D, nf.METRIC_INNER_PRODUCT)
-    index.add_global(xb)
-    xq_dev = torch.from_numpy(xq).cuda()
-    xq_pin = torch.from_numpy(xq).pin_memory()
-    index.local.path = {"auto": _lib.PATH_AUTO, "tc": _lib.PATH_TC, "tc1": _lib.PATH_TC1}[args.path]
-    planes = index.local._query_planes()
+    path_id = {"auto": _lib.PATH_AUTO, "tc": _lib.PATH_TC, "tc1": _lib.PATH_TC1}[args.path]
     one_pass = args.path in ("auto", "tc1")
 
-    def step_device():
-        q = nf.PackedMatrix.from_tensor(xq_dev, planes=planes)  # K0 on the fresh query batch
-        return index.search(q, K)
+    # Decompositions for N > 1 (the job stays config 1: 50,000 queries x 364,047 items):
+    #  "queries": the packed catalog (1.1 GB) is replicated on every GPU and the query batch is
+    #             split into N contiguous slices -- no data-path collective (the headline);
+    #  "catalog": north_star item 4 -- catalog rows sharded, every rank searches all queries on
+    #             its shard, NCCL all-gather of the per-shard (D, I) + K4 merge on every rank.
+    def q_slice(n):
+        per = (n + world - 1) // world
+        return min(n, rank * per), min(n, (rank + 1) * per)
 
-    def step_e2e():
-        xd = xq_pin.cuda(non_blocking=True)  # H2D from pinned host memory
-        q = nf.PackedMatrix.from_tensor(xd, planes=planes)
-        Dd, Id = index.search(q, K)
-        return nf._to_host(Dd), nf._to_host(Id)  # D2H into pinned buffers + stream sync
+    def build(mode):
+        if mode == "catalog" and world > 1:
+            idx = ShardedIndexFlat(D, nf.METRIC_INNER_PRODUCT)
+            idx.add_global(xb)
+            idx.local.path = path_id
+            lo, hi = 0, NQ
+            planes = idx.local._query_planes()
+            search = lambda q: idx.search(q, K)  # noqa: E731
+            rows = idx.local.ntotal
+        else:
+            idx = nf.IndexFlatIP(D)
+            idx.add(xb)
+            idx.path = path_id
+            lo, hi = q_slice(NQ) if world > 1 else (0, NQ)
+            planes = idx._query_planes()
+            search = lambda q: idx.search_packed(q, K)  # noqa: E731
+            rows = idx.ntotal
+        xq_dev = torch.from_numpy(xq[lo:hi]).cuda()
+        xq_pin = torch.from_numpy(xq[lo:hi]).pin_memory()
+
+        def step_device():
+            q = nf.PackedMatrix.from_tensor(xq_dev, planes=planes)  # K0 on the fresh query batch
+            return search(q)
+
+        def step_e2e():
+            xd = xq_pin.cuda(non_blocking=True)  # H2D from pinned host memory
+            q = nf.PackedMatrix.from_tensor(xd, planes=planes)
+            Dd, Id = search(q)
+            return nf._to_host(Dd), nf._to_host(Id)  # D2H into pinned buffers + stream sync
+
+        return dict(step_device=step_device, step_e2e=step_e2e, lo=lo, hi=hi, rows=rows, mode=mode)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -217,52 +243,64 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident timing
-    for _ in range(args.warmup):
-        step_device()
-    sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    _lib.profile_enable(True)
-    _lib.profile_read()
-    n0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        Dd, Id = step_device()
-    ev1.record()
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - n0
-    kern_ms, kern_n = _lib.profile_read()
-    _lib.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    def measure(run, sampler=None):
+        for _ in range(args.warmup):
+            run["step_device"]()
+        sync_all()
+        if sampler is not None:
+            sampler.start()
+        _lib.profile_enable(True)
+        _lib.profile_read()
+        n0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            run["step_device"]()
+        ev1.record()
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        launches = _lib.launch_count() - n0
+        kern_ms, kern_n = _lib.profile_read()
+        _lib.profile_enable(False)
+        clocks = sampler.stop() if sampler is not None else None
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # end to end through the public API with host buffers
+        for _ in range(max(1, min(args.warmup, 3))):
+            run["step_e2e"]()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            Dh, Ih = run["step_e2e"]()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(ms=ms, launches=launches, kern_ms=kern_ms, kern_n=kern_n, clocks=clocks,
+                    e2e_s=float(t.item()), Dh=Dh, Ih=Ih)
 
-    # ---- end to end through the public API with host buffers
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        Dh, Ih = step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    main_mode = args.shard if world > 1 else "queries"
+    run = build(main_mode)
+    res = measure(run, ClockSampler(local) if rank == 0 else None)
+    ms, launches, kern_ms, kern_n, clocks, e2e_s = (res[k] for k in ("ms", "launches", "kern_ms", "kern_n", "clocks", "e2e_s"))
+    Dh, Ih = res["Dh"], res["Ih"]
+    run = dict(lo=run["lo"], hi=run["hi"], rows=run["rows"], mode=main_mode)  # drop the index (frees HBM)
+    alt = None
+    if world > 1 and args.alt:
+        alt_mode = "catalog" if main_mode == "queries" else "queries"
+        torch.cuda.empty_cache()
+        r2 = measure(build(alt_mode))
+        alt = {"decomposition": alt_mode, "value": NQ * args.steps / (r2["ms"] / 1e3), "ms_per_step": r2["ms"] / args.steps,
+               "e2e": NQ * args.steps / r2["e2e_s"], "kernel_ms_avg": r2["kern_ms"] / max(1, r2["kern_n"])}
 
     if rank == 0:
         pk = peaks()
         value = NQ * args.steps / (ms / 1e3)
         # roofline of the dominant kernel (topk_tc_kernel): algorithmic flops of this rank's shard
-        shard_rows = index.local.ntotal
-        alg = 2.0 * NQ * shard_rows * D
+        alg = 2.0 * (run["hi"] - run["lo"]) * run["rows"] * D  # this rank's share of the job
         kavg_s = kern_ms / max(1, kern_n) / 1e3
         achieved = alg / kavg_s / 1e12 if kavg_s > 0 else 0.0
         tf32_peak = pk["tf32_sustained"]
@@ -288,8 +326,8 @@ def run_ours(args):
         # correctness spot check inside the bench: a query sample against the oracle
         from oracle import faiss_oracle as fo
         fo.build()
-        ns = 512
-        Do, Io = fo.knn_fast(xq[:ns], xb, K, 0)
+        ns = min(512, run["hi"] - run["lo"])
+        Do, Io = fo.knn_fast(xq[run["lo"]:run["lo"] + ns], xb, K, 0)
         rep = compare_topk(Dh[:ns], Ih[:ns], Do, Io, 0)
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -298,15 +336,19 @@ def run_ours(args):
             "dtype": ("f32 (1xTF32 tcgen05 filter + exact fp32 rescoring)" if one_pass
                       else "f32 (3xTF32 tcgen05, fp32 accumulate)"),
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "k": K, "parallelism": f"catalog row-sharded over {world} GPU(s)",
+            "config": {"workload": WORKLOAD, "k": K,
+                       "parallelism": ("single GPU" if world == 1 else
+                                       (f"queries split over {world} GPUs, packed catalog (1.1 GB) replicated, no data-path collective"
+                                        if main_mode == "queries" else
+                                        f"catalog row-sharded over {world} GPUs, NCCL all-gather + K4 merge")),
                        "l2": "inputs larger than L2 (catalog hi+lo planes 746 MB per full catalog)",
                        "path": args.path, "fallback_queries": int(_lib.lib.nrb_fallback_query_count()),
                        "timed": "K0 query split + K2 tcgen05 distance/selection + select" + (" + exact refine" if one_pass else "") +
-                                (" + NCCL all-gather + K4 merge" if world > 1 else "")},
+                                (" + NCCL all-gather + K4 merge" if (world > 1 and main_mode == "catalog") else "")},
             "roofline": roof,
             "e2e": {"value": NQ * args.steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": NQ * D * 4, "d2h_bytes_per_step": NQ * K * 12},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "other_decomposition": alt,
             "parity_sample": {"queries": ns, "ok": rep["ok"], "recall_at_50": rep["recall"],
                               "exact_ordered": rep["exact_ordered"], "max_rel_score_err": rep["max_rel_score_err"]},
         }
@@ -338,6 +380,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shard", default="queries", choices=["queries", "catalog"],
+                    help="N > 1: split the query batch (catalog replicated; default) or shard the catalog "
+                         "(north_star item 4: per-shard top-k + NCCL all-gather + merge)")
+    ap.add_argument("--no-alt", dest="alt", action="store_false",
+                    help="N > 1: do not also time the other decomposition")
     ap.add_argument("--path", default="auto", choices=["auto", "tc", "tc1"],
                     help="auto/tc1 = 1xTF32 filter + exact refine (default), tc = 3xTF32")
     args = ap.parse_args()
