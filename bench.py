@@ -223,17 +223,23 @@ def run_ours(args):
             search = lambda q: idx.search_packed(q, K)  # noqa: E731
             rows = idx.ntotal
         xq_dev = torch.from_numpy(xq[lo:hi]).cuda()
-        xq_pin = torch.from_numpy(xq[lo:hi]).pin_memory()
+        # host side of the end-to-end leg: page-locked query batch and result arrays, handed to
+        # the public API as numpy arrays (faiss's search(x, k, D, I) convention)
+        xq_pin = torch.from_numpy(xq[lo:hi]).pin_memory().numpy()
+        D_pin = torch.empty((hi - lo, K), dtype=torch.float32, pin_memory=True).numpy()
+        I_pin = torch.empty((hi - lo, K), dtype=torch.int64, pin_memory=True).numpy()
 
         def step_device():
             q = nf.PackedMatrix.from_tensor(xq_dev, planes=planes)  # K0 on the fresh query batch
             return search(q)
 
         def step_e2e():
-            xd = xq_pin.cuda(non_blocking=True)  # H2D from pinned host memory
-            q = nf.PackedMatrix.from_tensor(xd, planes=planes)
-            Dd, Id = search(q)
-            return nf._to_host(Dd), nf._to_host(Id)  # D2H into pinned buffers + stream sync
+            if mode == "catalog" and world > 1:
+                xd = torch.from_numpy(xq_pin).cuda(non_blocking=True)  # H2D from pinned host memory
+                q = nf.PackedMatrix.from_tensor(xd, planes=planes)
+                Dd, Id = search(q)
+                return nf._to_host_pair(Dd, Id, D_pin, I_pin)  # D2H + stream sync
+            return idx.search(xq_pin, K, D=D_pin, I=I_pin)  # the call a user makes: numpy in, numpy out
 
         return dict(step_device=step_device, step_e2e=step_e2e, lo=lo, hi=hi, rows=rows, mode=mode)
 

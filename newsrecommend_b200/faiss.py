@@ -67,11 +67,31 @@ def _to_device_f32(x):
     return t, from_np
 
 
-def _to_host(t: torch.Tensor) -> np.ndarray:
-    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    out.copy_(t, non_blocking=True)
+def _to_host(t: torch.Tensor, out: np.ndarray | None = None) -> np.ndarray:
+    """Device -> host. `out`: caller-provided array (faiss's search(x, k, D=None, I=None)
+    convention); page-locked memory makes the copy a single async DMA."""
+    if out is not None:
+        assert out.shape == tuple(t.shape) and out.flags.c_contiguous, "bad output array"
+        torch.from_numpy(out).copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return out.numpy()
+    return buf.numpy()
+
+
+def _to_host_pair(D: torch.Tensor, I: torch.Tensor, Do=None, Io=None):
+    """Both result arrays with one synchronisation."""
+    if Do is None:
+        Do = torch.empty(D.shape, dtype=D.dtype, pin_memory=True).numpy()
+    if Io is None:
+        Io = torch.empty(I.shape, dtype=I.dtype, pin_memory=True).numpy()
+    assert Do.shape == tuple(D.shape) and Io.shape == tuple(I.shape) and Do.dtype == np.float32 and Io.dtype == np.int64
+    torch.from_numpy(Do).copy_(D, non_blocking=True)
+    torch.from_numpy(Io).copy_(I, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return Do, Io
 
 
 class PackedMatrix:
@@ -199,17 +219,19 @@ class IndexFlat:
     def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0):
         return _search_flat_dev(q, self._packed(), self.metric_type, k, id_base, self.path)
 
-    def search(self, x, k: int):
+    def search(self, x, k: int, D=None, I=None):
+        """(D, I) = search(x, k). Like faiss, optional preallocated numpy outputs D f32[nq,k],
+        I i64[nq,k] are filled and returned (page-locked buffers avoid a staging copy)."""
         t, from_np = _to_device_f32(x)
         assert t.shape[1] == self.d
         assert k > 0
         if k > _lib.MAX_K:
             raise RuntimeError(f"k={k} > {_lib.MAX_K} is not supported by the selection stage")
         q = PackedMatrix.from_tensor(t, planes=self._query_planes())
-        D, I = self.search_packed(q, int(k))
-        if from_np:
-            return _to_host(D), _to_host(I)
-        return D, I
+        Dd, Id = self.search_packed(q, int(k))
+        if from_np or D is not None or I is not None:
+            return _to_host_pair(Dd, Id, D, I)
+        return Dd, Id
 
     def _query_planes(self):
         if self.path in (PATH_AUTO, PATH_TC1):
@@ -515,5 +537,5 @@ class IndexIVFFlat:
                                          self.metric_type, int(k), D[q0:q1].data_ptr(), I[q0:q1].data_ptr(),
                                          ws.data_ptr(), wsb, self.path, _stream()), "ivf_search")
         if from_np:
-            return _to_host(D), _to_host(I)
+            return _to_host_pair(D, I)
         return D, I
