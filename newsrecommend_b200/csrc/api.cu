@@ -104,15 +104,19 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     int best = 1;
     if (p.tail_pairs > 0) {
         int max_split = nbt < 64 ? nbt : 64;
-        const double ideal = (double)p.tail_pairs / C;
+        // cost of a plan = waves x (chunk length + per-unit overhead), in catalogs per CTA pair;
+        // a unit costs about 16 tiles on top of its item rows (query-tile load, threshold
+        // warm-up, 32 final prunes per warp), which is what stops tiny batches from being cut
+        // into dozens of slivers
+        const double ov = 16.0 / nbt;
         double best_cost = 1e30;
         for (int s = 1; s <= max_split; s++) {
-            const double cost = (double)(((int64_t)p.tail_pairs * s + C - 1) / C) / s;  // catalogs per CTA pair
+            const double waves = (double)(((int64_t)p.tail_pairs * s + C - 1) / C);
+            const double cost = waves * (1.0 / s + ov);
             if (cost < best_cost * 0.97) {  // prefer fewer splits unless >3% better
                 best_cost = cost;
                 best = s;
             }
-            if (cost <= ideal * 1.02) break;
         }
     }
     const int tiles_per = (nbt + best - 1) / best;
