@@ -96,7 +96,7 @@ int nrb_normalize_l2(float* x, int64_t n, int32_t d, int64_t ldx, void* stream);
  * L2 ascending squared distance clamped at 0), I i64[nq,k] = row index + id_base; missing
  * results are I = -1, D = -FLT_MAX (IP) / +FLT_MAX (L2). 1 <= k <= NRB_MAX_K.
  * path: NRB_PATH_AUTO picks NRB_PATH_TC1 when its preconditions hold (raw + hi + norms planes on
- * both sides, b->max_norm, kp <= 256, k <= 96), else NRB_PATH_TC. NRB_PATH_TC1 synchronises the
+ * both sides, b->max_norm, kp <= 256, k <= 112), else NRB_PATH_TC. NRB_PATH_TC1 synchronises the
  * stream once per call (it reads back the number of flagged queries). */
 size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp);
 int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,

@@ -144,7 +144,7 @@ struct FlatWs {
 static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int path) {
     Carver c(ws);
     FlatWs w;
-    const int pw = path == NRB_PATH_TC1 ? k + TC1_EXTRA : k;  // partial row width
+    const int pw = path == NRB_PATH_TC1 ? tc1_pw(k) : k;  // partial row width
     w.units = c.take<Unit>(p.n_units);
     w.n_units = c.take<int>(1);
     w.src = c.take<int>((size_t)nq * p.S);
@@ -396,7 +396,7 @@ extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, i
     // take the largest over the paths so that `path` can be chosen per call
     size_t best = 0;
     for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC1}) {
-        if (path == NRB_PATH_TC1 && k + TC1_EXTRA > 128) continue;
+        if (path == NRB_PATH_TC1 && !tc1_k_ok(k)) continue;
         FlatPlan p = plan_flat(nq, nb, k, path);
         size_t t = carve_flat(nullptr, p, nq, k, path).total;
         best = t > best ? t : best;
@@ -412,7 +412,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     if (path == NRB_PATH_AUTO) path = tc1_eligible(q, b, k) ? NRB_PATH_TC1 : NRB_PATH_TC;
     if (path == NRB_PATH_TC1 && !tc1_eligible(q, b, k)) {
         set_error("search_flat: NRB_PATH_TC1 needs raw/hi/norms planes on both sides, max_norm on the item "
-                  "side, kp <= 256 and k <= %d", 128 - TC1_EXTRA);
+                  "side, kp <= 256 and k <= %d", TC1_MAX_PW - TC1_MIN_EXTRA);
         return NRB_ERR_INVALID;
     }
     if (path != NRB_PATH_TC1) path = resolve_path(path);
@@ -439,7 +439,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         return launch_select(w.part_key, w.part_idx, w.src, p.S, q->n, k, metric, nullptr, id_base, D, I, st);
     }
     // ---- 1xTF32 filter + exact refine, then the 3xTF32 kernel for whatever was flagged
-    const int pw = k + TC1_EXTRA;
+    const int pw = tc1_pw(k);
     const float eps_xmax = TC1_EPS * b->max_norm;
     NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
     {

@@ -36,7 +36,11 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
 // 1xTF32 filter + exact refine (NRB_PATH_TC1): partial rows are `pw` = k + TC1_EXTRA wide and hold
 // every candidate within the error margin of the k-th; row_flags[a_row] = 1 marks rows whose
 // margin set did not fit. margin_scale = 2 * eps * max|x| (the kernel multiplies by |q|).
-constexpr int TC1_EXTRA = 32;
+constexpr int TC1_EXTRA = 32;      // margin slots per row when they fit ...
+constexpr int TC1_MIN_EXTRA = 16;  // ... never fewer than this (partial rows are at most 128 wide)
+constexpr int TC1_MAX_PW = 128;
+static inline int tc1_pw(int k) { return k + TC1_EXTRA <= TC1_MAX_PW ? k + TC1_EXTRA : TC1_MAX_PW; }
+static inline int tc1_k_ok(int k) { return k + TC1_MIN_EXTRA <= TC1_MAX_PW; }
 constexpr float TC1_EPS = 1.1f / 1024.f;  // both operands rounded to tf32 (2 * 2^-11) + accumulation slack
 int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,

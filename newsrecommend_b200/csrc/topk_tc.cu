@@ -849,14 +849,14 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
 
 int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
     return a->hi && b->hi && a->raw && b->raw && a->norms && b->norms && b->max_norm > 0.f &&
-           a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && k + TC1_EXTRA <= 128;
+           a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && tc1_k_ok(k);
 }
 
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, cudaStream_t st) {
-    NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", 128 - TC1_EXTRA);
+    NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
     NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - 64, "tc1: bad kp / pw");
     NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
     if (scratch_bytes < tc_scratch_bytes(grid)) {

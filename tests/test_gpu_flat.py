@@ -60,8 +60,8 @@ def test_golden_fixture(nf, path, metric):
     (130, 7, 12, 10), (5, 1, 40, 3), (1000, 20000, 250, 128),
 ])
 def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
-    if path == "tc1" and (k > 96 or d > 256):
-        pytest.skip("NRB_PATH_TC1 covers k <= 96 and d <= 256 (PATH_AUTO routes the rest to 3xTF32)")
+    if path == "tc1" and (k > 112 or d > 256):
+        pytest.skip("NRB_PATH_TC1 covers k <= 112 and d <= 256 (PATH_AUTO routes the rest to 3xTF32)")
     rng = np.random.default_rng(nq * 1000 + nb + d + k)
     xb = rng.standard_normal((nb, d), dtype=np.float32)
     xq = rng.standard_normal((nq, d), dtype=np.float32)
