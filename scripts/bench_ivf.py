@@ -11,6 +11,8 @@ from oracle import faiss_oracle as fo
 
 NLISTS = [int(a) for a in sys.argv[1:]] or [250]
 NQ = int(os.environ.get("NRB_IVF_NQ", "250000"))
+L2 = os.environ.get("NRB_IVF_METRIC", "ip") == "l2"
+MET = 1 if L2 else 0
 xb, topics = synth.g_skew(synth.N_ARTICLES, 250, 42, return_topics=True)
 xq = synth.user_profiles(xb, topics, NQ, 44)
 xb_d, xq_d = torch.from_numpy(xb).cuda(), torch.from_numpy(xq).cuda()
@@ -20,11 +22,11 @@ def timed(fn, reps=1):
     for _ in range(reps): out = fn()
     torch.cuda.synchronize(); return out, (time.perf_counter() - t0) / reps
 
-flat = nf.IndexFlatIP(250); flat.add(xb_d)
+flat = (nf.IndexFlatL2 if L2 else nf.IndexFlatIP)(250); flat.add(xb_d)
 (_, I_exact), t_flat = timed(lambda: flat.search(xq_d[:20000], 50))
 for nlist in NLISTS:
-    quant = nf.IndexFlatIP(250)
-    ivf = nf.IndexIVFFlat(quant, 250, nlist, nf.METRIC_INNER_PRODUCT)
+    quant = (nf.IndexFlatL2 if L2 else nf.IndexFlatIP)(250)
+    ivf = nf.IndexIVFFlat(quant, 250, nlist, MET)
     _, t_train = timed(lambda: ivf.train(xb_d))
     _, t_add = timed(lambda: ivf.add(xb_d))
     sizes = ivf.list_sizes()
@@ -41,13 +43,13 @@ for nlist in NLISTS:
     del qp
     # teacher-forced parity sample: oracle IVF with the same centroids and list contents
     cent = quant.reconstruct_n()
-    qo = fo.IndexFlatIP(250); qo.add(cent)
-    ivf_o = fo.IndexIVFFlat(qo, 250, nlist, fo.METRIC_INNER_PRODUCT); ivf_o.train(xb); ivf_o.add(xb); ivf_o.nprobe = 16
+    qo = (fo.IndexFlatL2 if L2 else fo.IndexFlatIP)(250); qo.add(cent)
+    ivf_o = fo.IndexIVFFlat(qo, 250, nlist, MET); ivf_o.train(xb); ivf_o.add(xb); ivf_o.nprobe = 16
     ns = 2048
     t0 = time.perf_counter(); Do, Io = ivf_o.search(xq[:ns], 50); t_cpu = time.perf_counter() - t0
-    rep = compare_topk(D[:ns].cpu().numpy(), I[:ns].cpu().numpy(), Do, Io, 0)
+    rep = compare_topk(D[:ns].cpu().numpy(), I[:ns].cpu().numpy(), Do, Io, MET)
     same_lists = bool(np.array_equal(sizes, ivf_o.list_sizes()))
-    print(json.dumps(dict(nlist=nlist, nq=NQ, nprobe=16, k=50, train_s=t_train, niter=ivf.cp.niter, add_s=t_add,
+    print(json.dumps(dict(metric="l2" if L2 else "ip", nlist=nlist, nq=NQ, nprobe=16, k=50, train_s=t_train, niter=ivf.cp.niter, add_s=t_add,
                           search_s=t_search, search_qps=NQ / t_search, scan_kernel_ms=kms, scan_kernel_launches=kn,
                           scanned_rows=scanned, scan_alg_tflop=2.0 * scanned * 250 / 1e12,
                           scanned_frac_of_flat=scanned / (NQ * float(synth.N_ARTICLES)),
