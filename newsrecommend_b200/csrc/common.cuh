@@ -123,11 +123,12 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
 // is set when more than keep_max entries were within the margin (the row is then incomplete
 // and must be recomputed by the exact path). margin = 0, keep_max = width = k is the plain
 // top-k prune. All 32 lanes must call with identical arguments.
+// R = registers per lane: the sort covers 32*R entries, so n (and width) must be <= 32*R.
+template <int R = CAND_CAP / 32>
 __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi, int n, int k, float margin,
                                                   int keep_max, int width, float* ok, int* oi, int lane,
                                                   int* kept, bool* overflow, float floor_thr = NEG_INF,
                                                   float* kth_out = nullptr) {
-    constexpr int R = CAND_CAP / 32;
     uint64_t c[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {

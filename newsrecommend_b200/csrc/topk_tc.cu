@@ -73,12 +73,74 @@ constexpr size_t V2_SMEM = (size_t)V2_STAGES * V2_STAGE_BYTES + sizeof(TcShared<
 // ---------------------------------------------------------------------------- epilogue
 struct EpiRow {
     int cnt;
+    int base;      // entries kept by the row's last prune (nothing was appended while cnt == base)
     float thr;     // append threshold: kth - margin (NEG_INF until k candidates exist)
     float qn;      // squared query norm (L2 keys, margins)
     float margin;  // 0 for the 3xTF32 kernels; error margin of the 1xTF32 filter
     int flag;      // set when more than keep_max candidates fell inside the margin
     unsigned* gslot;  // the query's shared running lower bound of its k-th key (ordered uint), or null
 };
+
+struct PruneOut {
+    float thr, kth;
+    int kept, ovf;
+};
+
+// One row's prune behind a real call: the kernel has three call sites (in-tile overflow guard,
+// scheduled prune, unit end) and two sort widths; inlining all of them multiplies the unrolled
+// bitonic networks and the kernel no longer fits the instruction cache.
+__device__ __noinline__ PruneOut prune_row_call(const float* bk, const int* bi, int n, int k, float margin,
+                                                int keep_max, int width, float* ok, int* oi, float floor_thr) {
+    const int lane = threadIdx.x & 31;
+    PruneOut o;
+    bool ovf;
+    if (n <= 128 && width <= 128)
+        o.thr = warp_prune_row_m<4>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
+    else
+        o.thr = warp_prune_row_m<CAND_CAP / 32>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf,
+                                                floor_thr, &o.kth);
+    o.ovf = ovf ? 1 : 0;
+    return o;
+}
+
+// Prunes the rows of the warp named by `need` (one bit per lane = row) back to their best k
+// (+ margin set), in place, and raises their thresholds.
+__device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float* ck, int* ci, int k, int keep_max,
+                                               int lane) {
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n = __shfl_sync(0xffffffffu, st.cnt, src);
+        const float mg = __shfl_sync(0xffffffffu, st.margin, src);
+        const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
+        float* rk = ck + (int64_t)src * CAND_CAP;
+        int* ri = ci + (int64_t)src * CAND_CAP;
+        const PruneOut o = prune_row_call(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, fl);
+        if (lane == src) {
+            st.cnt = o.kept;
+            st.base = o.kept;
+            st.thr = o.thr;
+            st.flag |= o.ovf;
+            if (st.gslot && o.kth > NEG_INF) atomicMax(st.gslot, ordered_u32(o.kth));
+        }
+    }
+}
+
+// f[i] for a run-time i, as five levels of selects: a dynamically indexed register array would be
+// placed in local memory, and with 227 KB of the SM's 256 KB configured as shared memory nearly
+// every local access is an L2 round trip on the epilogue's critical path.
+__device__ __forceinline__ float pick32(const float (&f)[32], int i) {
+    float a[16], b[8], c[4];
+    const bool s4 = (i & 16) != 0, s3 = (i & 8) != 0, s2 = (i & 4) != 0, s1 = (i & 2) != 0, s0 = (i & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) a[j] = s4 ? f[16 + j] : f[j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) b[j] = s3 ? a[8 + j] : a[j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = s2 ? b[4 + j] : b[j];
+    const float d0 = s1 ? c[2] : c[0], d1 = s1 ? c[3] : c[1];
+    return s0 ? d1 : d0;
+}
 
 // One 128 x 256 accumulator: thread = query row, 8 chunks of 32 columns.
 //   taddr0  TMEM address of (this warp's lane quarter, accumulator column 0)
@@ -96,9 +158,7 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
         ptx::tmem_ld_wait();
-        // Branch-free pass mask (bit i: column c0+i beats the row's threshold). A warp-chunk of
-        // 1,024 scores nearly always holds a few candidates, so there is no cheap "nothing to
-        // do" exit; what matters is that the common work is straight-line code.
+        // Branch-free pass mask (bit i: column c0+i beats the row's threshold).
         float f[32];
         uint32_t mask = 0;
 #pragma unroll
@@ -109,41 +169,28 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
             f[i] = x;
             mask |= (x > st.thr) ? (1u << i) : 0u;
         }
-        if (mask) {
-            // rare per lane (a few % of lanes per chunk): spill the 32 keys so that the set bits
-            // can be walked with a dynamic index
-            float sp[32];
+        if (__all_sync(0xffffffffu, mask == 0xffffffffu)) {
+            // cold rows (first tile of a unit): everything passes, static indices
+            float* dk = myk + st.cnt;
+            int* di = myi + st.cnt;
 #pragma unroll
-            for (int i = 0; i < 32; i++) sp[i] = f[i];
+            for (int i = 0; i < 32; i++) {
+                dk[i] = f[i];
+                di[i] = id0 + c0 + i;
+            }
+            st.cnt += 32;
+        } else if (mask) {
             do {
                 const int i = __ffs(mask) - 1;
                 mask &= mask - 1;
-                myk[st.cnt] = sp[i];
+                myk[st.cnt] = pick32(f, i);
                 myi[st.cnt] = id0 + c0 + i;
                 st.cnt++;
             } while (mask);
         }
-        unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
-        while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const int n = __shfl_sync(0xffffffffu, st.cnt, src);
-            const float mg = __shfl_sync(0xffffffffu, st.margin, src);
-            const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
-            float* rk = ck + (int64_t)src * CAND_CAP;
-            int* ri = ci + (int64_t)src * CAND_CAP;
-            int kept;
-            bool ovf;
-            float kth;
-            const float tnew = warp_prune_row_m(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, lane, &kept, &ovf,
-                                                fl, &kth);
-            if (lane == src) {
-                st.cnt = kept;
-                st.thr = tnew;
-                st.flag |= ovf ? 1 : 0;
-                if (st.gslot && kth > NEG_INF) atomicMax(st.gslot, ordered_u32(kth));
-            }
-        }
+        // overflow guard (rare once the prune schedule below is running)
+        const unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
+        if (need) epi_prune_rows(need, st, ck, ci, k, keep_max, lane);
     }
 }
 
@@ -156,14 +203,11 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
         const float mg = __shfl_sync(0xffffffffu, st.margin, src);
         const float fl = __shfl_sync(0xffffffffu, st.thr, src);
         const int64_t o = (prow0 + src) * pw;
-        int kept;
-        bool ovf;
-        float kth;
-        warp_prune_row_m(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, mg, pw, pw,
-                         part_key + o, part_idx + o, lane, &kept, &ovf, fl < __builtin_huge_valf() ? fl : NEG_INF, &kth);
+        const PruneOut r = prune_row_call(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, mg, pw, pw,
+                                          part_key + o, part_idx + o, fl < __builtin_huge_valf() ? fl : NEG_INF);
         if (lane == src) {
-            st.flag |= ovf ? 1 : 0;
-            if (st.gslot && kth > NEG_INF) atomicMax(st.gslot, ordered_u32(kth));
+            st.flag |= r.ovf;
+            if (st.gslot && r.kth > NEG_INF) atomicMax(st.gslot, ordered_u32(r.kth));
         }
     }
 }
@@ -220,10 +264,10 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
     int* ci = A.cand_idx_buf + crow0 * CAND_CAP;
     float* myk = ck + (int64_t)lane * CAND_CAP;
     int* myi = ci + (int64_t)lane * CAND_CAP;
-    uint32_t tempty_remote[2] = {0, 0};
+    uint32_t tempty_remote0 = 0, tempty_remote1 = 0;  // scalars: an indexed array would live in local memory
     if (PAIR) {
-        tempty_remote[0] = ptx::mapa_u32(&tempty[0], 0);
-        tempty_remote[1] = ptx::mapa_u32(&tempty[1], 0);
+        tempty_remote0 = ptx::mapa_u32(&tempty[0], 0);
+        tempty_remote1 = ptx::mapa_u32(&tempty[1], 0);
     }
     const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -238,6 +282,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         const bool live = row < un.a_rows && ar < A.a_total;
         EpiRow st;
         st.cnt = 0;
+        st.base = 0;
         st.thr = live ? NEG_INF : __builtin_huge_valf();
         st.qn = ((L2 || NEED_QN) && live) ? A.a_norms[ar] : 0.f;
         st.margin = NEED_QN ? A.margin_scale * sqrtf(st.qn) * (L2 ? 2.f : 1.f) : 0.f;
@@ -270,9 +315,20 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             __syncwarp();
             if (lane == 0) {
                 if (PAIR)
-                    ptx::mbar_arrive_cluster_relaxed(tempty_remote[acc]);
+                    ptx::mbar_arrive_cluster_relaxed(acc ? tempty_remote1 : tempty_remote0);
                 else
                     ptx::mbar_arrive(&tempty[acc]);
+            }
+            // Scheduled prune, after the accumulator went back: at tile counts 1, 2, 4, 8, ... every
+            // warp of the CTA pair brings all of its rows back to their best k and tightens their
+            // thresholds. A row's pass rate is ~k/n after n items, so each doubling admits ~k new
+            // candidates per row: buffers stay near 2k entries (the 128-entry sort) and, because the
+            // 16 warps that share every accumulator hand-off prune in the SAME tiles, the hand-offs
+            // in between never wait for a straggler in the middle of a 256-entry sort.
+            const uint32_t tp = (uint32_t)t + 1u;
+            if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles) {
+                const unsigned need = __ballot_sync(0xffffffffu, st.cnt > st.base);
+                if (need) epi_prune_rows(need, st, ck, ci, A.k, A.pw, lane);
             }
         }
         epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
@@ -564,7 +620,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 // true top-k. select_refine_kernel rescoring those <= k+32 candidates exactly in fp32 gives
 // the final order; rows with more candidates than slots are flagged and recomputed by the
 // 3xTF32 kernel.
-constexpr int V3_STAGES = 5;
+constexpr int V3_STAGES = 6;
 constexpr int V3_MAX_NKC = 8;
 constexpr int V3_A_BYTES = V3_MAX_NKC * A_BYTES;  // 128 KB resident query tile
 
@@ -579,7 +635,8 @@ struct Tc3Shared {
     uint32_t pad;
     float nrm[EPI_WGS][2][HALF_N];
 };
-constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared) + 1024;
+constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared);  // no slack: __align__(1024)
+static_assert(V3_SMEM <= 232448, "topk_tc3_kernel exceeds the 227 KB of shared memory per CTA");
 
 template <bool L2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -590,8 +647,9 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf,
                 unsigned* __restrict__ gthr) {
     constexpr int STAGES = V3_STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;  // 128-byte swizzled tiles need 1024-byte alignment
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* smem_b = smem + V3_A_BYTES;
     Tc3Shared* sh = reinterpret_cast<Tc3Shared*>(smem_b + (size_t)STAGES * BH_BYTES);
 
@@ -857,7 +915,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, cudaStream_t st) {
     NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
-    NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - 64, "tc1: bad kp / pw");
+    NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - HALF_N, "tc1: bad kp / pw");
     NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
     if (scratch_bytes < tc_scratch_bytes(grid)) {
         set_error("tc1: scratch too small");

@@ -31,7 +31,7 @@ for nlist in NLISTS:
     _, t_add = timed(lambda: ivf.add(xb_d))
     sizes = ivf.list_sizes()
     ivf.nprobe = 16
-    ivf.search(xq_d[:4096], 50)  # warm-up (allocator, lists build)
+    ivf.search(xq_d, 50)  # warm-up at full size (lists build, allocator growth for the workspaces)
     _lib.profile_enable(True); _lib.profile_read()
     (D, I), t_search = timed(lambda: ivf.search(xq_d, 50))
     kms, kn = _lib.profile_read(); _lib.profile_enable(False)
