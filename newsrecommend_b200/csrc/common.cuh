@@ -181,6 +181,76 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
     return fmaxf(thr, floor_thr);  // threshold for further appends
 }
 
+// Cheap mid-unit prune: instead of sorting, find a LOWER BOUND lb of the row's k-th best key by
+// bisection on the ordered-uint keys (count(key >= lb) is between k and k + slack, or exactly the
+// k-th after 32 halvings), then keep every entry with key >= max(lb - margin, floor_thr) by
+// stream compaction (order not preserved; ties are all kept, so no (key, idx) tie rule is
+// needed here -- the exact sort at the end of the unit applies it). Dropped entries are below
+// a valid bound of the k-th minus the margin, hence outside the final top-k / margin set.
+// Returns the new append threshold; *kept = entries left in (bk, bi); *lb_u = ordered-uint lower
+// bound of the k-th (0 while fewer than k entries exist). n <= 32*R. All lanes call together.
+template <int R>
+__device__ __forceinline__ float warp_tighten_row(float* bk, int* bi, int n, int k, float margin, float floor_thr,
+                                                  int lane, int* kept, uint32_t* lb_u) {
+    constexpr int SLACK = 3;
+    uint32_t u[R];
+    int id[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const int e = i * 32 + lane;
+        const bool valid = e < n;
+        u[i] = valid ? ordered_u32(bk[e]) : 0u;  // 0 sorts below every float
+        id[i] = valid ? bi[e] : -1;
+    }
+    __syncwarp();
+    uint32_t lo = 0;
+    if (n >= k) {
+        uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            mn = (u[i] != 0u && u[i] < mn) ? u[i] : mn;
+            mx = u[i] > mx ? u[i] : mx;
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        // invariant: count(u >= lo) >= k > count(u >= hi)
+        lo = mn;
+        uint32_t hi = mx + 1u;
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < R; i++) c += (u[i] >= mid) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= k) {
+                lo = mid;
+                if (c <= k + SLACK) break;
+            } else {
+                hi = mid;
+            }
+        }
+    }
+    *lb_u = lo;
+    const float thr = fmaxf(from_ordered_u32(lo) - margin, floor_thr);  // lo == 0 -> NEG_INF
+    const uint32_t lt = (1u << lane) - 1u;
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const float key = from_ordered_u32(u[i]);
+        const bool keep = (u[i] != 0u) && key >= thr;
+        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = base + __popc(b & lt);
+            bk[pos] = key;
+            bi[pos] = id[i];
+        }
+        base += __popc(b);
+    }
+    __syncwarp();
+    *kept = base;
+    return thr;
+}
+
 // Plain top-k prune (margin 0): keeps min(n, k) entries, returns kth.
 __device__ __forceinline__ float warp_prune_row(const float* bk, const int* bi, int n, int k,
                                                 float* ok, int* oi, int lane) {

@@ -103,8 +103,26 @@ __device__ __noinline__ PruneOut prune_row_call(const float* bk, const int* bi, 
     return o;
 }
 
-// Prunes the rows of the warp named by `need` (one bit per lane = row) back to their best k
-// (+ margin set), in place, and raises their thresholds.
+// Mid-unit prune of one row, in place: the bisection/compaction fast path, and the exact sort only
+// when that leaves too many entries (heavy ties, or a margin set that does not fit).
+constexpr int TIGHTEN_MAX_KEEP = 160;
+__device__ __noinline__ PruneOut tighten_row_call(float* bk, int* bi, int n, int k, float margin, int keep_max,
+                                                  float floor_thr) {
+    const int lane = threadIdx.x & 31;
+    PruneOut o;
+    uint32_t lb;
+    if (n <= 128)
+        o.thr = warp_tighten_row<4>(bk, bi, n, k, margin, floor_thr, lane, &o.kept, &lb);
+    else
+        o.thr = warp_tighten_row<CAND_CAP / 32>(bk, bi, n, k, margin, floor_thr, lane, &o.kept, &lb);
+    o.kth = from_ordered_u32(lb);
+    o.ovf = 0;
+    if (o.kept > TIGHTEN_MAX_KEEP) o = prune_row_call(bk, bi, o.kept, k, margin, keep_max, keep_max, bk, bi, o.thr);
+    return o;
+}
+
+// Prunes the rows of the warp named by `need` (one bit per lane = row) back to (about) their best
+// k (+ margin set), in place, and raises their thresholds.
 __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float* ck, int* ci, int k, int keep_max,
                                                int lane) {
     while (need) {
@@ -115,7 +133,7 @@ __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float*
         const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
         float* rk = ck + (int64_t)src * CAND_CAP;
         int* ri = ci + (int64_t)src * CAND_CAP;
-        const PruneOut o = prune_row_call(rk, ri, n, k, mg, keep_max, keep_max, rk, ri, fl);
+        const PruneOut o = tighten_row_call(rk, ri, n, k, mg, keep_max, fl);
         if (lane == src) {
             st.cnt = o.kept;
             st.base = o.kept;
