@@ -193,8 +193,9 @@ def run_ours(args):
     from newsrecommend_b200.sharded import ShardedIndexFlat
 
     xb, xq = make_data()
-    path_id = {"auto": _lib.PATH_AUTO, "tc": _lib.PATH_TC, "tc1": _lib.PATH_TC1}[args.path]
-    one_pass = args.path in ("auto", "tc1")
+    path_id = {"auto": _lib.PATH_AUTO, "tc": _lib.PATH_TC, "tc1": _lib.PATH_TC1, "tc16": _lib.PATH_TC16}[args.path]
+    one_pass = args.path in ("auto", "tc1", "tc16")
+    f16 = args.path in ("auto", "tc16")
 
     # Decompositions for N > 1 (the job stays config 1: 50,000 queries x 364,047 items):
     #  "queries": the packed catalog (1.1 GB) is replicated on every GPU and the query batch is
@@ -211,7 +212,7 @@ def run_ours(args):
             idx.add_global(xb)
             idx.local.path = path_id
             lo, hi = 0, NQ
-            planes = idx.local._query_planes()
+            planes = idx.local._query_planes(K)
             search = lambda q: idx.search(q, K)  # noqa: E731
             rows = idx.local.ntotal
         else:
@@ -219,7 +220,7 @@ def run_ours(args):
             idx.add(xb)
             idx.path = path_id
             lo, hi = q_slice(NQ) if world > 1 else (0, NQ)
-            planes = idx._query_planes()
+            planes = idx._query_planes(K)
             search = lambda q: idx.search_packed(q, K)  # noqa: E731
             rows = idx.ntotal
         xq_dev = torch.from_numpy(xq[lo:hi]).cuda()
@@ -311,23 +312,36 @@ def run_ours(args):
         achieved = alg / kavg_s / 1e12 if kavg_s > 0 else 0.0
         tf32_peak = pk["tf32_sustained"]
         passes = 1.0 if one_pass else 3.0
-        peak = tf32_peak / passes
+        if f16:
+            # fp16 operands run at the bf16 rate: the denominator is MEASURED_PEAKS' dense bf16 figure
+            # (sustained: the kernel is timed inside back-to-back steps)
+            peak = pk["bf16_sustained"]
+            kname = ("topk_tc3_kernel<IP, fp16> (tcgen05 kind::f16 filter on power-of-two scaled fp16 planes "
+                     "with error margin; exact fp32 refine follows)")
+            note = ("peak = MEASURED_PEAKS (%s) dense bf16/fp16 sustained %.1f TFLOP/s (burst %.1f); cuBLAS TF32 "
+                    "sustained on this pool %.1f" % (pk["src"], pk["bf16_sustained"], pk["bf16"], tf32_peak))
+            pipe_frac = achieved * 256.0 / 250.0 / pk["bf16_sustained"]
+        else:
+            peak = tf32_peak / passes
+            kname = ("topk_tc3_kernel<IP> (tcgen05 1xTF32 filter with error margin; exact fp32 refine follows)"
+                     if one_pass else "topk_tc2_kernel<IP> (tcgen05 3xTF32 + fused selection)")
+            note = ("peak = cuBLAS TF32 sustained %.1f TFLOP/s (scripts/gpu_probe.py, same method as "
+                    "MEASURED_PEAKS.json; profiles/r01_probe.json) / %d TF32 pass(es) per product; "
+                    "MEASURED_PEAKS (%s) bf16 sustained %.1f" % (tf32_peak, int(passes), pk["src"], pk["bf16_sustained"]))
+            pipe_frac = achieved * passes * 256.0 / 250.0 / tf32_peak
         roof = {
             "bound": "tensor",
-            "kernel": ("topk_tc3_kernel<IP> (tcgen05 1xTF32 filter with error margin; exact fp32 refine follows)"
-                       if one_pass else "topk_tc2_kernel<IP> (tcgen05 3xTF32 + fused selection)"),
+            "kernel": kname,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_note": ("peak = cuBLAS TF32 sustained %.1f TFLOP/s (scripts/gpu_probe.py, same method as "
-                          "MEASURED_PEAKS.json; profiles/r01_probe.json) / %d TF32 pass(es) per product; "
-                          "MEASURED_PEAKS (%s) bf16 sustained %.1f" % (tf32_peak, int(passes), pk["src"], pk["bf16_sustained"])),
-            "tensor_pipe_frac": achieved * passes * 256.0 / 250.0 / tf32_peak,
+            "peak_note": note,
+            "tensor_pipe_frac": pipe_frac,
             "frac_of_bf16_peak": achieved / pk["bf16_sustained"],
             "kernel_ms_avg": kavg_s * 1e3, "kernel_launches_timed": kern_n,
             "alg_flop_per_launch": alg,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at N = 1
             # (ncu --set full, profiles/r01_ncu_full_tc3_final.csv: 7.53 GB + 1.22 GB); the
             # 3xTF32 kernel was captured before the last planner change (profiles/r01_ncu_full_prof_tc2.csv)
-            "traffic": (8.75e9 if one_pass else 50.2e9) if world == 1 else None,
+            "traffic": (None if f16 else 8.75e9 if one_pass else 50.2e9) if world == 1 else None,
         }
         # correctness spot check inside the bench: a query sample against the oracle
         from oracle import faiss_oracle as fo
@@ -339,7 +353,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": ("f32 (1xTF32 tcgen05 filter + exact fp32 rescoring)" if one_pass
+            "dtype": ("f32 (fp16 tcgen05 filter with a proven error margin + exact fp32 rescoring)" if f16 else
+                      "f32 (1xTF32 tcgen05 filter + exact fp32 rescoring)" if one_pass
                       else "f32 (3xTF32 tcgen05, fp32 accumulate)"),
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "k": K,
@@ -391,8 +406,9 @@ def main():
                          "(north_star item 4: per-shard top-k + NCCL all-gather + merge)")
     ap.add_argument("--no-alt", dest="alt", action="store_false",
                     help="N > 1: do not also time the other decomposition")
-    ap.add_argument("--path", default="auto", choices=["auto", "tc", "tc1"],
-                    help="auto/tc1 = 1xTF32 filter + exact refine (default), tc = 3xTF32")
+    ap.add_argument("--path", default="auto", choices=["auto", "tc", "tc1", "tc16"],
+                    help="auto/tc16 = fp16 filter + exact fp32 refine (default), tc1 = the same with the 1xTF32 "
+                         "filter, tc = 3xTF32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.out = _StdoutGuard()

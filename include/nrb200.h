@@ -35,6 +35,8 @@ extern "C" {
 #define NRB_PATH_TC 2   /* tcgen05 3xTF32 kernels */
 #define NRB_PATH_TC1 3  /* tcgen05 1xTF32 filter with a rigorous error margin + exact fp32 refine;
                            flat search only, rows that overflow the margin set fall back to TC */
+#define NRB_PATH_TC16 4 /* the same filter + refine on power-of-two scaled IEEE fp16 planes (11-bit
+                           significand like tf32, hence the same margin) at twice the tensor rate */
 
 #define NRB_MAX_K 128 /* largest k / nprobe supported by the selection stage */
 
@@ -43,7 +45,11 @@ extern "C" {
  *   hi   [n, kp]  tf32(raw)            (cvt.rna, low 13 mantissa bits zero)
  *   lo   [n, kp]  tf32(raw - hi)
  *   norms[n]      squared L2 norms (fp32)
- * raw feeds the SIMT kernels, hi/lo feed the 3xTF32 tcgen05 kernels via TMA. */
+ *   h16  [n, kp]  fp16(raw * s), s a power of two chosen so that |row| * s < 2^15: one s for the
+ *                 whole matrix on the item side (h16_scale), one per row on the query side
+ *                 (h16_row_scale); see nrb_pack_rows_h16
+ * raw feeds the SIMT kernels and the exact refine, hi/lo feed the 3xTF32 tcgen05 kernels via
+ * TMA, hi alone the 1xTF32 filter, h16 the fp16 filter. */
 typedef struct nrb_matrix {
     const float* raw;
     const float* hi;
@@ -53,8 +59,10 @@ typedef struct nrb_matrix {
     int32_t d;
     int32_t kp;
     float max_norm; /* max row L2 norm (not squared) over the matrix, 0 = unknown; needed on the
-                       item side by NRB_PATH_TC1 */
-    int32_t reserved;
+                       item side by NRB_PATH_TC1 / NRB_PATH_TC16 */
+    float h16_scale; /* item side: the power of two every row of h16 was multiplied by (0 = none) */
+    const void* h16; /* [n, kp] IEEE fp16 = raw * scale (NRB_PATH_TC16), or NULL */
+    const float* h16_row_scale; /* query side: per-row power-of-two scales f32[n] of h16, or NULL */
 } nrb_matrix;
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
@@ -81,6 +89,13 @@ int nrb_profile_read(double* total_ms, int* n_launches);
  * norms may be NULL. */
 int nrb_pack_rows(const float* x, int64_t n, int32_t d, int64_t ldx, int32_t kp, float* raw,
                   float* hi, float* lo, float* norms, void* stream);
+/* fp16 plane of NRB_PATH_TC16: h16[i, :] = fp16(x[i, :] * s_i), zero-padded to kp columns.
+ * uniform_scale > 0: s_i = uniform_scale for every row (item side; the caller guarantees
+ * max|row| * uniform_scale <= 65504 -- newsrecommend_b200 uses 2^(14 - floor(log2(max_norm)))).
+ * uniform_scale == 0: s_i = 2^(14 - floor(log2(|x_i|))) per row (1 for a zero row), written to
+ * row_scale f32[n] (query side). */
+int nrb_pack_rows_h16(const float* x, int64_t n, int32_t d, int64_t ldx, int32_t kp, float uniform_scale,
+                      void* h16, float* row_scale, void* stream);
 /* dst[i, :] = src[idx[i], :] for rows of `width` floats (width % 4 == 0). Builds the
  * list-contiguous IVF planes (ArrayInvertedLists, Retrieval.py:23) and query groups. */
 int nrb_gather_rows(const float* src, int32_t width, const int32_t* idx, int64_t n, float* dst,
@@ -95,9 +110,11 @@ int nrb_normalize_l2(float* x, int64_t n, int32_t d, int64_t ldx, void* stream);
  * search inside Clustering::train (Retrieval.py:18). D f32[nq,k] best-first (IP descending,
  * L2 ascending squared distance clamped at 0), I i64[nq,k] = row index + id_base; missing
  * results are I = -1, D = -FLT_MAX (IP) / +FLT_MAX (L2). 1 <= k <= NRB_MAX_K.
- * path: NRB_PATH_AUTO picks NRB_PATH_TC1 when its preconditions hold (raw + hi + norms planes on
- * both sides, b->max_norm, kp <= 256, k <= 112), else NRB_PATH_TC. NRB_PATH_TC1 synchronises the
- * stream once per call (it reads back the number of flagged queries). */
+ * path: NRB_PATH_AUTO picks NRB_PATH_TC16 when its preconditions hold (raw + h16 + norms planes and
+ * scales on both sides, b->max_norm, kp <= 256, k <= 112), else NRB_PATH_TC1 (hi instead of h16),
+ * else NRB_PATH_TC. The filter paths synchronise the stream once per call (they read back the
+ * number of flagged queries); flagged queries are recomputed by NRB_PATH_TC, for which the lo
+ * planes must be present or q->raw / b->hi,lo (the query rows are split on the fly). */
 size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp);
 int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
                     int64_t id_base, float* D, int64_t* I, void* workspace,

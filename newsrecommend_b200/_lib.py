@@ -14,14 +14,14 @@ LIB_PATH = os.path.join(_PKG, "libnrb200.so")
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
-PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1 = 0, 1, 2, 3
+PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1, PATH_TC16 = 0, 1, 2, 3, 4
 MAX_K = 128
 
 # every symbol include/nrb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "nrb_version", "nrb_last_error", "nrb_device_info", "nrb_launch_count",
     "nrb_profile_enable", "nrb_profile_read", "nrb_set_tc_variant",
-    "nrb_pack_rows", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
+    "nrb_pack_rows", "nrb_pack_rows_h16", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
     "nrb_search_flat_workspace", "nrb_search_flat", "nrb_fallback_query_count",
     "nrb_kmeans_update_workspace", "nrb_kmeans_update",
     "nrb_rand_perm_host", "nrb_split_clusters_host",
@@ -35,7 +35,7 @@ class Matrix(C.Structure):
     """struct nrb_matrix"""
     _fields_ = [("raw", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p), ("norms", C.c_void_p),
                 ("n", C.c_int64), ("d", C.c_int32), ("kp", C.c_int32), ("max_norm", C.c_float),
-                ("reserved", C.c_int32)]
+                ("h16_scale", C.c_float), ("h16", C.c_void_p), ("h16_row_scale", C.c_void_p)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -56,6 +56,7 @@ lib.nrb_profile_enable.argtypes = [C.c_int]
 lib.nrb_set_tc_variant.argtypes = [C.c_int]
 lib.nrb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
 lib.nrb_pack_rows.argtypes = [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]
+lib.nrb_pack_rows_h16.argtypes = [_vp, _i64, _i32, _i64, _i32, C.c_float, _vp, _vp, _vp]
 lib.nrb_gather_rows.argtypes = [_vp, _i32, _vp, _i64, _vp, _vp]
 lib.nrb_gather_i64.argtypes = [_vp, _vp, _i64, _vp, _vp]
 lib.nrb_normalize_l2.argtypes = [_vp, _i64, _i32, _i64, _vp]

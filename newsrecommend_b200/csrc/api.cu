@@ -144,7 +144,8 @@ struct FlatWs {
 static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int path) {
     Carver c(ws);
     FlatWs w;
-    const int pw = path == NRB_PATH_TC1 ? tc1_pw(k) : k;  // partial row width
+    const bool filt = path == NRB_PATH_TC1 || path == NRB_PATH_TC16;
+    const int pw = filt ? tc1_pw(k) : k;  // partial row width
     w.units = c.take<Unit>(p.n_units);
     w.n_units = c.take<int>(1);
     w.src = c.take<int>((size_t)nq * p.S);
@@ -152,7 +153,7 @@ static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int pat
     w.part_idx = c.take<int>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
     w.flags = w.flag_list = w.flag_count = nullptr;
     w.gthr = path == NRB_PATH_SIMT ? nullptr : c.take<unsigned>(nq);
-    if (path == NRB_PATH_TC1) {
+    if (filt) {
         w.flags = c.take<int>(nq);
         w.flag_list = c.take<int>(nq);
         w.flag_count = c.take<int>(1);
@@ -395,7 +396,7 @@ extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, i
     if (nq <= 0 || k <= 0 || k > NRB_MAX_K) return 256;
     // take the largest over the paths so that `path` can be chosen per call
     size_t best = 0;
-    for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC1}) {
+    for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC1}) {  // TC16 carves like TC1
         if (path == NRB_PATH_TC1 && !tc1_k_ok(k)) continue;
         FlatPlan p = plan_flat(nq, nb, k, path);
         size_t t = carve_flat(nullptr, p, nq, k, path).total;
@@ -409,13 +410,20 @@ namespace nrb {
 static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric, int k, int64_t id_base,
                             float* D, int64_t* I, void* workspace, size_t workspace_bytes, int path,
                             cudaStream_t st) {
-    if (path == NRB_PATH_AUTO) path = tc1_eligible(q, b, k) ? NRB_PATH_TC1 : NRB_PATH_TC;
+    if (path == NRB_PATH_AUTO)
+        path = tc16_eligible(q, b, k) ? NRB_PATH_TC16 : tc1_eligible(q, b, k) ? NRB_PATH_TC1 : NRB_PATH_TC;
     if (path == NRB_PATH_TC1 && !tc1_eligible(q, b, k)) {
         set_error("search_flat: NRB_PATH_TC1 needs raw/hi/norms planes on both sides, max_norm on the item "
                   "side, kp <= 256 and k <= %d", TC1_MAX_PW - TC1_MIN_EXTRA);
         return NRB_ERR_INVALID;
     }
-    if (path != NRB_PATH_TC1) path = resolve_path(path);
+    if (path == NRB_PATH_TC16 && !tc16_eligible(q, b, k)) {
+        set_error("search_flat: NRB_PATH_TC16 needs raw/h16/norms planes and h16 scales on both sides, max_norm on "
+                  "the item side, kp <= 256 and k <= %d", TC1_MAX_PW - TC1_MIN_EXTRA);
+        return NRB_ERR_INVALID;
+    }
+    const bool filt = path == NRB_PATH_TC1 || path == NRB_PATH_TC16;
+    if (!filt) path = resolve_path(path);
     const FlatPlan p = plan_flat(q->n, b->n, k, path);
     const FlatWs w = carve_flat(workspace, p, q->n, k, path);
     if (!workspace || workspace_bytes < w.total) {
@@ -426,7 +434,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.full_pairs, p.tail_pairs,
                                      p.tsplit, p.chunk_rows, p.wgs, st))) return rc;
     if (w.gthr) NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
-    if (path != NRB_PATH_TC1) {
+    if (!filt) {
         {
             ProfScope prof(st);
             if (path == NRB_PATH_SIMT)
@@ -438,14 +446,14 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         if (rc) return rc;
         return launch_select(w.part_key, w.part_idx, w.src, p.S, q->n, k, metric, nullptr, id_base, D, I, st);
     }
-    // ---- 1xTF32 filter + exact refine, then the 3xTF32 kernel for whatever was flagged
+    // ---- 1xTF32 / fp16 filter + exact refine, then the 3xTF32 kernel for whatever was flagged
     const int pw = tc1_pw(k);
     const float eps_xmax = TC1_EPS * b->max_norm;
     NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
     {
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
-                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, st);
+                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, path == NRB_PATH_TC16, st);
     }
     if (rc) return rc;
     if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
@@ -455,26 +463,36 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     NRB_CUDA_CHECK(cudaMemcpyAsync(&nflag, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     NRB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (nflag == 0) return NRB_OK;
-    NRB_REQUIRE(q->lo && b->lo, "search_flat: %d queries need the 3xTF32 fallback but the lo planes are missing", nflag);
+    NRB_REQUIRE(b->hi && b->lo && ((q->hi && q->lo) || q->raw),
+                "search_flat: %d queries need the 3xTF32 fallback but the item hi/lo planes are missing", nflag);
     g_fallback_queries += nflag;
     const size_t plane = (size_t)nflag * q->kp * sizeof(float);
     const size_t wsb2 = nrb_search_flat_workspace(nflag, b->n, k, q->kp);
     char* tmp = nullptr;
-    const size_t tmp_bytes = 2 * align_up(plane, 256) + align_up((size_t)nflag * 4, 256) +
+    const size_t tmp_bytes = 3 * align_up(plane, 256) + align_up((size_t)nflag * 4, 256) +
                              align_up((size_t)nflag * k * 4, 256) + align_up((size_t)nflag * k * 8, 256) + wsb2;
     NRB_CUDA_CHECK(cudaMallocAsync((void**)&tmp, tmp_bytes, st));
     Carver c(tmp);
     float* fhi = c.take<float>((size_t)nflag * q->kp);
     float* flo = c.take<float>((size_t)nflag * q->kp);
+    float* fraw = c.take<float>((size_t)nflag * q->kp);
     float* fnr = c.take<float>(nflag);
     float* Df = c.take<float>((size_t)nflag * k);
     int64_t* If = c.take<int64_t>((size_t)nflag * k);
     void* ws2 = c.take<char>(wsb2);
-    rc = launch_gather_rows(q->hi, q->kp, w.flag_list, 1, nflag, fhi, st);
-    if (!rc) rc = launch_gather_rows(q->lo, q->kp, w.flag_list, 1, nflag, flo, st);
+    if (q->hi && q->lo) {
+        rc = launch_gather_rows(q->hi, q->kp, w.flag_list, 1, nflag, fhi, st);
+        if (!rc) rc = launch_gather_rows(q->lo, q->kp, w.flag_list, 1, nflag, flo, st);
+    } else {
+        // the filter paths pack queries without hi/lo planes: split the flagged raw rows here
+        rc = launch_gather_rows(q->raw, q->kp, w.flag_list, 1, nflag, fraw, st);
+        if (!rc) rc = launch_pack_rows(fraw, nflag, q->kp, q->kp, q->kp, nullptr, fhi, flo, nullptr, st);
+    }
     if (!rc) rc = launch_gather_scalar(q->norms, w.flag_list, 1, nflag, fnr, st);
     nrb_matrix qf = *q;
     qf.raw = nullptr;
+    qf.h16 = nullptr;
+    qf.h16_row_scale = nullptr;
     qf.hi = fhi;
     qf.lo = flo;
     qf.norms = fnr;
@@ -495,7 +513,7 @@ extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t
     NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "search_flat: k=%d out of range [1,%d]", k, NRB_MAX_K);
     NRB_REQUIRE(q->d == b->d && q->kp == b->kp, "search_flat: dimension mismatch (%d/%d vs %d/%d)", q->d, q->kp, b->d, b->kp);
     NRB_REQUIRE(q->n >= 0 && b->n >= 0 && b->n < (1LL << 31) - 4096 && q->n < (1LL << 31), "search_flat: sizes out of range");
-    NRB_REQUIRE(path >= NRB_PATH_AUTO && path <= NRB_PATH_TC1, "search_flat: bad path %d", path);
+    NRB_REQUIRE(path >= NRB_PATH_AUTO && path <= NRB_PATH_TC16, "search_flat: bad path %d", path);
     if (q->n == 0) return NRB_OK;
     int rc = require_device();
     if (rc) return rc;

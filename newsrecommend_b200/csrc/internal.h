@@ -43,10 +43,13 @@ static inline int tc1_pw(int k) { return k + TC1_EXTRA <= TC1_MAX_PW ? k + TC1_E
 static inline int tc1_k_ok(int k) { return k + TC1_MIN_EXTRA <= TC1_MAX_PW; }
 constexpr float TC1_EPS = 1.1f / 1024.f;  // both operands rounded to tf32 (2 * 2^-11) + accumulation slack
 int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
+// fp16 filter (NRB_PATH_TC16): same kernel and error bound (fp16 and tf32 both carry an 11-bit
+// significand) on power-of-two scaled fp16 planes, at twice the tensor rate.
+int tc16_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
-                        size_t scratch_bytes, unsigned* gthr, cudaStream_t st);
+                        size_t scratch_bytes, unsigned* gthr, int f16, cudaStream_t st);
 
 // ---- topk_simt.cu: fp32 CUDA-core distance + selection over the same Unit list
 size_t simt_scratch_bytes(int grid);
@@ -72,6 +75,8 @@ int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, 
 size_t counting_sort_ws(int64_t n, int nb);
 int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets, int* order,
                              int* pos_of, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_pack_rows(const float* x, int64_t n, int d, int64_t ldx, int kp, float* raw, float* hi, float* lo,
+                     float* norms, cudaStream_t st);
 int launch_gather_rows(const float* src, int width, const int32_t* idx, int div, int64_t n,
                        float* dst, cudaStream_t st);
 int launch_gather_scalar(const float* src, const int32_t* idx, int div, int64_t n, float* dst,

@@ -3,6 +3,8 @@
 // k-way merge (K4).
 #include <cfloat>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -39,6 +41,37 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, int64_t n, int d, 
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) norms[row] = acc;
+        }
+    }
+}
+
+// fp16 plane of the fp16 filter. One warp per row: h16[row, c] = fp16(x[row, c] * s), s a power
+// of two -- `uniform` when > 0, else 2^(14 - floor(log2(|row|))) (so |row| * s is in [2^14, 2^15)
+// and no element can overflow fp16), stored in row_scale[row].
+__global__ void pack_rows_h16_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, int kp,
+                                     float uniform, __half* __restrict__ h16, float* __restrict__ row_scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp0; row < n; row += nwarps) {
+        const float* xr = x + row * ldx;
+        float s = uniform;
+        if (!(uniform > 0.f)) {
+            float acc = 0.f;
+            for (int c = lane; c < d; c += 32) acc = fmaf(xr[c], xr[c], acc);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            // sqrt(acc) rounded up a little so that an fp32 sum that came out low cannot push an
+            // element past 2^15 * (1 + 2^-10) (far below the fp16 maximum anyway)
+            const float nr = sqrtf(acc);
+            int e = (nr > 0.f && nr < __builtin_huge_valf()) ? ilogbf(nr) : 14;
+            e = e < -60 ? -60 : (e > 60 ? 60 : e);
+            s = exp2f((float)(14 - e));
+            if (lane == 0 && row_scale) row_scale[row] = s;
+        }
+        for (int c = lane; c < kp; c += 32) {
+            const float v = (c < d) ? xr[c] * s : 0.f;
+            h16[row * kp + c] = __float2half_rn(v);
         }
     }
 }
@@ -663,7 +696,25 @@ extern "C" int nrb_pack_rows(const float* x, int64_t n, int32_t d, int64_t ldx, 
     return NRB_OK;
 }
 
+extern "C" int nrb_pack_rows_h16(const float* x, int64_t n, int32_t d, int64_t ldx, int32_t kp,
+                                 float uniform_scale, void* h16, float* row_scale, void* stream) {
+    NRB_REQUIRE(x && h16 && n >= 0 && d > 0 && kp >= d && kp % 32 == 0 && ldx >= d,
+                "pack_rows_h16: bad shape n=%lld d=%d kp=%d ldx=%lld", (long long)n, d, kp, (long long)ldx);
+    NRB_REQUIRE(uniform_scale > 0.f || row_scale, "pack_rows_h16: per-row scaling needs row_scale");
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_rows_h16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, d, ldx, kp, uniform_scale,
+                                                                            (__half*)h16, row_scale);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
 namespace nrb {
+int launch_pack_rows(const float* x, int64_t n, int d, int64_t ldx, int kp, float* raw, float* hi, float* lo,
+                     float* norms, cudaStream_t st) {
+    return nrb_pack_rows(x, n, d, ldx, kp, raw, hi, lo, norms, (void*)st);
+}
 int launch_gather_rows(const float* src, int width, const int32_t* idx, int div, int64_t n,
                        float* dst, cudaStream_t st) {
     if (n == 0) return NRB_OK;

@@ -183,6 +183,16 @@ __device__ __forceinline__ void umma_tf32_cg2(uint32_t d_tmem, uint64_t adesc, u
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, IEEE fp16 inputs (K = 16 per instruction), fp32 accumulate.
+__device__ __forceinline__ void umma_f16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive (once the issued MMAs retire) on the mbarrier at the same smem offset in every CTA of
 // `cta_mask`.
 __device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
@@ -243,6 +253,11 @@ __device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo) {
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with IEEE fp16 operands (a_format = b_format = 0), fp32 accumulate, K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

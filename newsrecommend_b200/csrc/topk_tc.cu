@@ -75,6 +75,9 @@ struct EpiRow {
     int cnt;
     int base;      // entries kept by the row's last prune (nothing was appended while cnt == base)
     float thr;     // append threshold: kth - margin (NEG_INF until k candidates exist)
+    float cthr;    // thr in the domain the pass mask compares in (IP: thr * sc, L2: thr)
+    float sc;      // accumulator = sc * (q . x): product of the operands' power-of-two fp16 scales, else 1
+    float inv;     // 1 / sc (exact)
     float qn;      // squared query norm (L2 keys, margins)
     float margin;  // 0 for the 3xTF32 kernels; error margin of the 1xTF32 filter
     int flag;      // set when more than keep_max candidates fell inside the margin
@@ -123,6 +126,7 @@ __device__ __noinline__ PruneOut tighten_row_call(float* bk, int* bi, int n, int
 
 // Prunes the rows of the warp named by `need` (one bit per lane = row) back to (about) their best
 // k (+ margin set), in place, and raises their thresholds.
+template <bool L2>
 __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float* ck, int* ci, int k, int keep_max,
                                                int lane) {
     while (need) {
@@ -138,6 +142,7 @@ __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float*
             st.cnt = o.kept;
             st.base = o.kept;
             st.thr = o.thr;
+            st.cthr = L2 ? o.thr : o.thr * st.sc;
             st.flag |= o.ovf;
             if (st.gslot && o.kth > NEG_INF) atomicMax(st.gslot, ordered_u32(o.kth));
         }
@@ -170,6 +175,7 @@ template <bool L2, bool FULL>
 __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
                                          float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                          int lane) {
+    const float m2inv = -2.f * st.inv;
 #pragma unroll 1
     for (int c0 = 0; c0 < HALF_N; c0 += 32) {  // taddr0 / id0 / nrm / valid are relative to the warpgroup's columns
         if (!FULL && c0 >= valid) break;  // warp-uniform
@@ -181,19 +187,20 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
         uint32_t mask = 0;
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-            float x = __uint_as_float(v[i]);
-            if (L2) x = -fmaxf(st.qn + nrm[c0 + i] - 2.f * x, 0.f);
+            float x = __uint_as_float(v[i]);  // IP: stays in the accumulator's (scaled) domain
+            if (L2) x = -fmaxf(fmaf(x, m2inv, st.qn + nrm[c0 + i]), 0.f);
             if (!FULL && c0 + i >= valid) x = NEG_INF;
             f[i] = x;
-            mask |= (x > st.thr) ? (1u << i) : 0u;
+            mask |= (x > st.cthr) ? (1u << i) : 0u;
         }
+        const float ksc = L2 ? 1.f : st.inv;  // stored keys are always unscaled
         if (__all_sync(0xffffffffu, mask == 0xffffffffu)) {
             // cold rows (first tile of a unit): everything passes, static indices
             float* dk = myk + st.cnt;
             int* di = myi + st.cnt;
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-                dk[i] = f[i];
+                dk[i] = f[i] * ksc;
                 di[i] = id0 + c0 + i;
             }
             st.cnt += 32;
@@ -201,14 +208,14 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, co
             do {
                 const int i = __ffs(mask) - 1;
                 mask &= mask - 1;
-                myk[st.cnt] = pick32(f, i);
+                myk[st.cnt] = pick32(f, i) * ksc;
                 myi[st.cnt] = id0 + c0 + i;
                 st.cnt++;
             } while (mask);
         }
         // overflow guard (rare once the prune schedule below is running)
         const unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
-        if (need) epi_prune_rows(need, st, ck, ci, k, keep_max, lane);
+        if (need) epi_prune_rows<L2>(need, st, ck, ci, k, keep_max, lane);
     }
 }
 
@@ -267,6 +274,9 @@ struct EpiArgs {
     unsigned* gthr;
     const int* row_map;
     int row_div;
+    // fp16 filter: accumulator = a_row_scale[row] * b_scale * (q . x), powers of two (null / 1: unscaled)
+    const float* a_row_scale;
+    float b_scale;
 };
 
 template <bool L2, bool PAIR, bool NEED_QN>
@@ -302,6 +312,9 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         st.cnt = 0;
         st.base = 0;
         st.thr = live ? NEG_INF : __builtin_huge_valf();
+        st.cthr = st.thr;
+        st.sc = (A.a_row_scale && live) ? A.a_row_scale[ar] * A.b_scale : 1.f;
+        st.inv = 1.f / st.sc;
         st.qn = ((L2 || NEED_QN) && live) ? A.a_norms[ar] : 0.f;
         st.margin = NEED_QN ? A.margin_scale * sqrtf(st.qn) * (L2 ? 2.f : 1.f) : 0.f;
         st.flag = 0;
@@ -322,7 +335,10 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             epi_stage_norms<L2>(nrm_t, A.b_norms, un, col_base, valid, A.b_total, etid, wg);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            if (st.gslot) st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
+            if (st.gslot) {
+                st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
+                st.cthr = L2 ? st.thr : st.thr * st.sc;
+            }
             const uint32_t taddr0 = taddr_wg + (uint32_t)(acc * BN);
             if (valid >= HALF_N)
                 epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
@@ -346,7 +362,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             const uint32_t tp = (uint32_t)t + 1u;
             if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles) {
                 const unsigned need = __ballot_sync(0xffffffffu, st.cnt > st.base);
-                if (need) epi_prune_rows(need, st, ck, ci, A.k, A.pw, lane);
+                if (need) epi_prune_rows<L2>(need, st, ck, ci, A.k, A.pw, lane);
             }
         }
         epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
@@ -477,7 +493,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     } else {
         // ------------------------------------------------------------------ selection epilogue
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, 0);
     }
 
@@ -615,7 +631,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     } else {
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
     }
 
@@ -656,15 +672,20 @@ struct Tc3Shared {
 constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared);  // no slack: __align__(1024)
 static_assert(V3_SMEM <= 232448, "topk_tc3_kernel exceeds the 227 KB of shared memory per CTA");
 
-template <bool L2>
+// F16: the operand planes are IEEE fp16 (same 11-bit significand as tf32, so the same error
+// bound) scaled by powers of two -- per row on the query side, one scale on the item side. K
+// chunks are still 128-byte rows (64 halves), four K = 16 MMAs each, at twice the tf32 rate and
+// half the shared-memory / L2 traffic.
+template <bool L2, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_bh,
                 const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc, int k, int pw,
                 float margin_scale, const float* __restrict__ a_norms, const float* __restrict__ b_norms,
                 int64_t a_total, int64_t b_total, float* __restrict__ part_key, int* __restrict__ part_idx,
                 int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf,
-                unsigned* __restrict__ gthr) {
+                unsigned* __restrict__ gthr, const float* __restrict__ a_row_scale, float b_scale) {
     constexpr int STAGES = V3_STAGES;
+    constexpr int KE = F16 ? 2 * KC : KC;  // elements per 128-byte K chunk
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;  // 128-byte swizzled tiles need 1024-byte alignment
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -715,7 +736,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             if (ptx::elect_one()) {
                 if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
                 for (int kc = 0; kc < nkc; kc++)
-                    ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KC, un.a_row0);
+                    ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KE, un.a_row0);
             }
             __syncwarp();
             a_phase ^= 1;
@@ -726,7 +747,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                     const uint32_t fb = full0_base + (uint32_t)stage * 8;
                     if (ptx::elect_one()) {
                         if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * BH_BYTES);
-                        ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BH_BYTES, &map_bh, fb, kc * KC, brow);
+                        ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BH_BYTES, &map_bh, fb, kc * KE, brow);
                     }
                     __syncwarp();
                     if (++stage == STAGES) {
@@ -739,7 +760,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * BM, BN);
+            constexpr uint32_t idesc = F16 ? ptx::umma_idesc_f16(2 * BM, BN) : ptx::umma_idesc_tf32(2 * BM, BN);
             const uint32_t la0 = ptx::umma_desc_lo(ptx::smem_u32(smem));
             const uint32_t lb0 = ptx::umma_desc_lo(ptx::smem_u32(smem_b));
             int stage = 0;
@@ -763,9 +784,14 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                         const uint32_t l_b = lb0 + (uint32_t)(stage * BH_BYTES) / 16;
                         if (ptx::elect_one()) {
 #pragma unroll
-                            for (int ks = 0; ks < KC / 8; ks++)
-                                ptx::umma_tf32_cg2(d_tmem, ptx::umma_desc_join(l_a + 2 * ks),
-                                                   ptx::umma_desc_join(l_b + 2 * ks), idesc, (kc | ks) != 0);
+                            for (int ks = 0; ks < 4; ks++) {  // 32 bytes of K per MMA: 8 tf32 / 16 fp16
+                                if (F16)
+                                    ptx::umma_f16_cg2(d_tmem, ptx::umma_desc_join(l_a + 2 * ks),
+                                                      ptx::umma_desc_join(l_b + 2 * ks), idesc, (kc | ks) != 0);
+                                else
+                                    ptx::umma_tf32_cg2(d_tmem, ptx::umma_desc_join(l_a + 2 * ks),
+                                                       ptx::umma_desc_join(l_b + 2 * ks), idesc, (kc | ks) != 0);
+                            }
                             ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);
                         }
                         __syncwarp();
@@ -787,7 +813,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     } else {
         // ------------------------------------------------------------------ filter epilogue (both CTAs)
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   row_flags, cand_key_buf, cand_idx_buf, gthr, nullptr, 1};
+                   row_flags, cand_key_buf, cand_idx_buf, gthr, nullptr, 1, a_row_scale, b_scale};
         epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
     }
 
@@ -835,6 +861,28 @@ int make_plane_map(CUtensorMap* m, const float* base, int64_t rows, int kp, int 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld kp=%d)", (int)r, (long long)rows, kp);
+        return NRB_ERR_CUDA;
+    }
+    return NRB_OK;
+}
+
+// Tensor map over a [rows, kp] fp16 plane: box = 64 columns (128 bytes) x box_rows rows, 128-byte
+// swizzle; a last chunk that sticks out of the row (kp % 64 != 0) is zero-filled by TMA.
+int make_plane_map_h16(CUtensorMap* m, const void* base, int64_t rows, int kp, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return NRB_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)(rows > 0 ? rows : 1)};
+    cuuint64_t gstr[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * KC), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp16) failed: CUresult %d (rows=%lld kp=%d)", (int)r, (long long)rows, kp);
         return NRB_ERR_CUDA;
     }
     return NRB_OK;
@@ -928,11 +976,19 @@ int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
            a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && tc1_k_ok(k);
 }
 
+int tc16_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
+    return a->h16 && a->h16_row_scale && b->h16 && b->h16_scale > 0.f && a->raw && b->raw && a->norms &&
+           b->norms && b->max_norm > 0.f && a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && tc1_k_ok(k);
+}
+
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
-                        size_t scratch_bytes, unsigned* gthr, cudaStream_t st) {
-    NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
+                        size_t scratch_bytes, unsigned* gthr, int f16, cudaStream_t st) {
+    if (f16)
+        NRB_REQUIRE(tc16_eligible(a, b, k), "tc16: not eligible (h16 planes + scales / raw / norms / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
+    else
+        NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
     NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - HALF_N, "tc1: bad kp / pw");
     NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
     if (scratch_bytes < tc_scratch_bytes(grid)) {
@@ -941,22 +997,39 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
     }
     CUtensorMap mah, mbh;
     int rc;
-    if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
-    if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN / 2))) return rc;
+    if (f16) {
+        if ((rc = make_plane_map_h16(&mah, a->h16, a->n, a->kp, BM))) return rc;
+        if ((rc = make_plane_map_h16(&mbh, b->h16, b->n, b->kp, BN / 2))) return rc;
+    } else {
+        if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
+        if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN / 2))) return rc;
+    }
     float* ck = (float*)scratch;
     int* ci = (int*)((char*)scratch + (size_t)grid * EPI_WGS * BM * CAND_CAP * sizeof(float));
-    const int nkc = a->kp / KC;
+    const int nkc = f16 ? (a->kp + 2 * KC - 1) / (2 * KC) : a->kp / KC;
+    const float* ars = f16 ? a->h16_row_scale : nullptr;
+    const float bsc = f16 ? b->h16_scale : 1.f;
+#define NRB_TC3_LAUNCH(L2V, F16V)                                                                                   \
+    do {                                                                                                            \
+        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<L2V, F16V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)V3_SMEM));                                                         \
+        topk_tc3_kernel<L2V, F16V><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw,      \
+                                                                      margin_scale, a->norms, b->norms, a->n, b->n, \
+                                                                      part_key, part_idx, row_flags, ck, ci, gthr,  \
+                                                                      ars, bsc);                                    \
+    } while (0)
     if (metric == NRB_METRIC_L2) {
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
-        topk_tc3_kernel<true><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
-                                                                  a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                  row_flags, ck, ci, gthr);
+        if (f16)
+            NRB_TC3_LAUNCH(true, true);
+        else
+            NRB_TC3_LAUNCH(true, false);
     } else {
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM));
-        topk_tc3_kernel<false><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
-                                                                   a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                   row_flags, ck, ci, gthr);
+        if (f16)
+            NRB_TC3_LAUNCH(false, true);
+        else
+            NRB_TC3_LAUNCH(false, false);
     }
+#undef NRB_TC3_LAUNCH
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

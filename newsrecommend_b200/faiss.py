@@ -15,11 +15,14 @@ from __future__ import annotations
 import ctypes as C
 import sys
 
+import math
+
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import METRIC_INNER_PRODUCT, METRIC_L2, PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1, Matrix, check, lib
+from ._lib import (METRIC_INNER_PRODUCT, METRIC_L2, PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1, PATH_TC16, Matrix,
+                   check, lib)
 
 __all__ = [
     "METRIC_INNER_PRODUCT", "METRIC_L2", "IndexFlat", "IndexFlatL2", "IndexFlatIP", "IndexHNSWFlat",
@@ -94,30 +97,47 @@ def _to_host_pair(D: torch.Tensor, I: torch.Tensor, Do=None, Io=None):
     return Do, Io
 
 
+def _h16_scale_for(max_norm: float) -> float:
+    """Power of two s with max_norm * s in [2^14, 2^15): no element of a row can overflow fp16."""
+    if not (max_norm > 0.0) or not math.isfinite(max_norm):
+        return 1.0
+    e = min(max(math.frexp(max_norm)[1] - 1, -60), 60)  # floor(log2(max_norm))
+    return float(2.0 ** (14 - e))
+
+
 class PackedMatrix:
-    """Device form of a row-major fp32 matrix: zero-padded raw rows, tf32 hi / lo planes and
-    squared norms (struct nrb_matrix). Grows geometrically on append."""
+    """Device form of a row-major fp32 matrix (struct nrb_matrix): zero-padded raw rows, tf32
+    hi / lo planes, squared norms and the scaled fp16 plane of the fp16 filter. Grows
+    geometrically on append. The fp16 plane carries ONE power-of-two scale for index storage
+    (track_max_norm=True; re-packed from the raw plane if a later append outgrows it) and one
+    scale per row for query batches."""
 
     def __init__(self, d: int, device=None, planes=("raw", "hi", "lo", "norms"), track_max_norm=False):
         self.d = d
         self.kp = _round_kp(d)
         self.n = 0
         self.device = device or _device()
-        self.planes = planes
+        self.planes = tuple(planes)
         self._cap = 0
-        self.raw = self.hi = self.lo = self.norms = None
-        # max row norm: the item side of the 1xTF32 filter (NRB_PATH_TC1) needs it; costs one
-        # small reduction + sync per append, so only index storage tracks it
+        self.raw = self.hi = self.lo = self.norms = self.h16 = self.row_scale = None
+        # max row norm: the item side of the filter paths needs it; costs one small reduction +
+        # sync per append, so only index storage tracks it
         self.track_max_norm = track_max_norm and "norms" in planes
         self.max_norm = 0.0
+        self.h16_scale = 0.0
+        if "h16" in self.planes and not self.track_max_norm:
+            self.planes = self.planes + ("row_scale",)
+        if "h16" in self.planes and self.track_max_norm:
+            assert "raw" in self.planes, "the uniform-scale fp16 plane is (re)built from the raw plane"
 
     def _reserve(self, n: int):
         if n <= self._cap:
             return
         cap = max(n, int(self._cap * 1.5), 128)
         for name in self.planes:
-            shape = (cap,) if name == "norms" else (cap, self.kp)
-            new = torch.empty(shape, dtype=torch.float32, device=self.device)
+            shape = (cap,) if name in ("norms", "row_scale") else (cap, self.kp)
+            dtype = torch.float16 if name == "h16" else torch.float32
+            new = torch.empty(shape, dtype=dtype, device=self.device)
             old = getattr(self, name)
             if old is not None and self.n:
                 new[: self.n].copy_(old[: self.n])
@@ -131,19 +151,35 @@ class PackedMatrix:
         self._reserve(self.n + m)
         if m:
             off = self.n
-            check(lib.nrb_pack_rows(
-                x.data_ptr(), m, self.d, x.stride(0), self.kp,
-                _ptr(self.raw[off:]) if self.raw is not None else 0,
-                _ptr(self.hi[off:]) if self.hi is not None else 0,
-                _ptr(self.lo[off:]) if self.lo is not None else 0,
-                _ptr(self.norms[off:]) if self.norms is not None else 0, _stream()), "pack_rows")
+            if any(p is not None for p in (self.raw, self.hi, self.lo, self.norms)):
+                check(lib.nrb_pack_rows(
+                    x.data_ptr(), m, self.d, x.stride(0), self.kp,
+                    _ptr(self.raw[off:]) if self.raw is not None else 0,
+                    _ptr(self.hi[off:]) if self.hi is not None else 0,
+                    _ptr(self.lo[off:]) if self.lo is not None else 0,
+                    _ptr(self.norms[off:]) if self.norms is not None else 0, _stream()), "pack_rows")
             if self.track_max_norm:
                 self.max_norm = max(self.max_norm, float(self.norms[off:off + m].max().sqrt()))
+            if self.h16 is not None:
+                if self.track_max_norm:
+                    # keep the current scale while the largest row still fits fp16 with headroom
+                    if self.h16_scale > 0.0 and self.max_norm * self.h16_scale <= 60000.0:
+                        lo_row, rows = off, m
+                    else:
+                        self.h16_scale = _h16_scale_for(self.max_norm)
+                        lo_row, rows = 0, off + m
+                    check(lib.nrb_pack_rows_h16(_ptr(self.raw[lo_row:]), rows, self.d, self.kp, self.kp,
+                                                self.h16_scale, _ptr(self.h16[lo_row:]), 0, _stream()), "pack_rows_h16")
+                else:
+                    check(lib.nrb_pack_rows_h16(x.data_ptr(), m, self.d, x.stride(0), self.kp, 0.0,
+                                                _ptr(self.h16[off:]), _ptr(self.row_scale[off:]), _stream()),
+                          "pack_rows_h16")
         self.n += m
 
     def clear(self):
         self.n = 0
         self.max_norm = 0.0
+        self.h16_scale = 0.0
 
     def struct(self, row0: int = 0, rows: int | None = None) -> Matrix:
         rows = self.n - row0 if rows is None else rows
@@ -152,6 +188,9 @@ class PackedMatrix:
         m.hi = _ptr(self.hi[row0:]) if self.hi is not None else None
         m.lo = _ptr(self.lo[row0:]) if self.lo is not None else None
         m.norms = _ptr(self.norms[row0:]) if self.norms is not None else None
+        m.h16 = _ptr(self.h16[row0:]) if self.h16 is not None else None
+        m.h16_row_scale = _ptr(self.row_scale[row0:]) if self.row_scale is not None else None
+        m.h16_scale = self.h16_scale if self.h16 is not None else 0.0
         m.n, m.d, m.kp = rows, self.d, self.kp
         m.max_norm = self.max_norm if self.track_max_norm else 0.0
         return m
@@ -179,6 +218,9 @@ def _search_flat_dev(q: PackedMatrix, b: PackedMatrix, metric: int, k: int, id_b
     return D, I
 
 
+_INDEX_PLANES = ("raw", "hi", "lo", "norms", "h16")
+
+
 # ------------------------------------------------------------------------------------ flat
 class IndexFlat:
     """IndexFlatL2 / IndexFlatIP (Retrieval.py:25-26,32). add() copies into HBM."""
@@ -188,8 +230,9 @@ class IndexFlat:
         self.metric_type = metric
         self.is_trained = True
         self.verbose = False
-        # PATH_AUTO: 1xTF32 filter + exact refine (PATH_TC1) when eligible, else 3xTF32 (PATH_TC);
-        # PATH_TC forces 3xTF32, PATH_SIMT the fp32 CUDA-core kernels
+        # PATH_AUTO: fp16 filter + exact fp32 refine (PATH_TC16) when eligible (d <= 256, k <= 112),
+        # else 3xTF32 (PATH_TC); PATH_TC1 = the same filter on the tf32 hi planes, PATH_TC forces
+        # 3xTF32, PATH_SIMT the fp32 CUDA-core kernels
         self.path = PATH_AUTO
         self._xb: PackedMatrix | None = None
 
@@ -204,7 +247,7 @@ class IndexFlat:
         t, _ = _to_device_f32(x)
         assert t.shape[1] == self.d
         if self._xb is None:
-            self._xb = PackedMatrix(self.d, t.device, track_max_norm=True)
+            self._xb = PackedMatrix(self.d, t.device, planes=_INDEX_PLANES, track_max_norm=True)
         self._xb.append(t)
 
     def reset(self):
@@ -213,7 +256,7 @@ class IndexFlat:
 
     def _packed(self) -> PackedMatrix:
         if self._xb is None:
-            self._xb = PackedMatrix(self.d, track_max_norm=True)
+            self._xb = PackedMatrix(self.d, planes=_INDEX_PLANES, track_max_norm=True)
         return self._xb
 
     def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0):
@@ -227,15 +270,20 @@ class IndexFlat:
         assert k > 0
         if k > _lib.MAX_K:
             raise RuntimeError(f"k={k} > {_lib.MAX_K} is not supported by the selection stage")
-        q = PackedMatrix.from_tensor(t, planes=self._query_planes())
+        q = PackedMatrix.from_tensor(t, planes=self._query_planes(int(k)))
         Dd, Id = self.search_packed(q, int(k))
         if from_np or D is not None or I is not None:
             return _to_host_pair(Dd, Id, D, I)
         return Dd, Id
 
-    def _query_planes(self):
-        if self.path in (PATH_AUTO, PATH_TC1):
-            return ("raw", "hi", "lo", "norms")  # lo only feeds the (rare) 3xTF32 fallback
+    def _query_planes(self, k: int = 1):
+        """Planes the chosen path reads on the query side (mirrors the eligibility rule of
+        nrb_search_flat; queries flagged by a filter are re-split from the raw plane)."""
+        filt_ok = _round_kp(self.d) <= 256 and k <= 112 and self._packed().max_norm > 0.0  # empty / all-zero index
+        if self.path == PATH_TC16 or (self.path == PATH_AUTO and filt_ok):
+            return ("raw", "norms", "h16")
+        if self.path == PATH_TC1:
+            return ("raw", "hi", "norms")
         need = ("raw",) if self.path == PATH_SIMT else ("hi", "lo")
         return need + (("norms",) if self.metric_type == METRIC_L2 else ())
 
@@ -461,7 +509,7 @@ class IndexIVFFlat:
         assert t.shape[1] == self.d
         if self._x is None:
             self._x = PackedMatrix(self.d, t.device, planes=("raw",))
-        q = PackedMatrix.from_tensor(t, planes=self.quantizer._query_planes())
+        q = PackedMatrix.from_tensor(t, planes=self.quantizer._query_planes(1))
         _, a = self.quantizer.search_packed(q, 1)
         a = a.reshape(-1)
         self._assign = a if self._assign is None or self._x.n == 0 else torch.cat([self._assign, a])
@@ -522,7 +570,7 @@ class IndexIVFFlat:
         elif nq:
             L = self._build_lists()
             planes = ("raw",) if self.path == PATH_SIMT else ("hi", "lo")
-            planes = tuple(dict.fromkeys(planes + self.quantizer._query_planes() +
+            planes = tuple(dict.fromkeys(planes + self.quantizer._query_planes(nprobe) +
                                          (("norms",) if self.metric_type == METRIC_L2 else ())))
             ls = L["packed"].struct()
             for q0 in range(0, nq, IVF_QUERY_BATCH):

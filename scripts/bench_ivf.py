@@ -37,7 +37,7 @@ for nlist in NLISTS:
     kms, kn = _lib.profile_read(); _lib.profile_enable(False)
     rec = recall_at_k(I[:20000].cpu().numpy(), I_exact.cpu().numpy())
     # rows actually scanned: sum over (query, probed list) of the list length
-    qp = nf.PackedMatrix.from_tensor(xq_d, planes=quant._query_planes())
+    qp = nf.PackedMatrix.from_tensor(xq_d, planes=quant._query_planes(16))
     _, coarse = quant.search_packed(qp, 16)
     scanned = int(torch.from_numpy(sizes).cuda()[coarse.reshape(-1)].sum().item())
     del qp

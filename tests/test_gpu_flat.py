@@ -10,7 +10,7 @@ from newsrecommend_b200.parity import compare_topk
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-PATHS = {"tc": 2, "simt": 1, "tc1": 3, "auto": 0}
+PATHS = {"tc": 2, "simt": 1, "tc1": 3, "tc16": 4, "auto": 0}
 
 
 def _l2_scale(xq, xb):
@@ -42,7 +42,39 @@ def test_pack_rows_split_is_exact(nf):
     assert np.allclose(p.norms[:1000].cpu().numpy(), (x.astype(np.float64) ** 2).sum(1), rtol=1e-5)
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "auto"])
+def test_pack_rows_h16_scales(nf):
+    """fp16 plane of the fp16 filter: power-of-two scales (per row for queries, one for index
+    storage, re-packed when a later append outgrows it), relative rounding error <= 2^-11."""
+    import torch
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((777, 250)) * np.exp(rng.uniform(-20, 20, size=(777, 1)))).astype(np.float32)
+    x[5] = 0
+    q = nf.PackedMatrix.from_tensor(torch.from_numpy(x).cuda(), planes=("raw", "norms", "h16"))
+    s = q.row_scale[:777].cpu().numpy().astype(np.float64)
+    h = q.h16[:777].cpu().numpy().astype(np.float64)
+    nrm = np.sqrt((x.astype(np.float64) ** 2).sum(1))
+    assert (np.log2(s) == np.round(np.log2(s))).all() and s[5] == 1.0
+    live = nrm > 0
+    assert ((nrm * s)[live] >= 2.0 ** 14 * (1 - 1e-6)).all() and ((nrm * s)[live] < 2.0 ** 15 * (1 + 1e-6)).all()
+    assert np.isfinite(h).all() and (h[:, 250:] == 0).all()
+    err = np.abs(h[:, :250] / s[:, None] - x)
+    assert (err <= np.abs(x) * 2.0 ** -11 + 2.0 ** -25 / s[:, None]).all()
+    # index storage: one scale; a 1000x larger second batch forces a re-pack of the first
+    b = nf.PackedMatrix(250, planes=("raw", "hi", "lo", "norms", "h16"), track_max_norm=True)
+    x1 = rng.standard_normal((300, 250), dtype=np.float32)
+    b.append(torch.from_numpy(x1).cuda())
+    s1 = b.h16_scale
+    x2 = x1 * np.float32(1000.0)
+    b.append(torch.from_numpy(x2).cuda())
+    s2 = b.h16_scale
+    assert s2 < s1 and b.max_norm * s2 < 2.0 ** 15 * (1 + 1e-6)
+    hb = b.h16[:600].cpu().numpy().astype(np.float64) / s2
+    xa = np.concatenate([x1, x2])
+    assert np.isfinite(hb).all()
+    assert (np.abs(hb[:, :250] - xa) <= np.abs(xa) * 2.0 ** -11 + 2.0 ** -25 / s2).all()
+
+
+@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "tc16", "auto"])
 @pytest.mark.parametrize("metric", [0, 1])
 def test_golden_fixture(nf, path, metric):
     g = np.load(os.path.join(GOLDEN, "flat_small.npz"))
@@ -52,7 +84,7 @@ def test_golden_fixture(nf, path, metric):
     assert rep["ok"], rep
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "auto"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "tc16", "auto"])
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("nq,nb,d,k", [
     (1, 5000, 250, 50), (19, 5000, 250, 50), (20, 5000, 256, 50), (129, 3001, 250, 20),
@@ -60,8 +92,8 @@ def test_golden_fixture(nf, path, metric):
     (130, 7, 12, 10), (5, 1, 40, 3), (1000, 20000, 250, 128),
 ])
 def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
-    if path == "tc1" and (k > 112 or d > 256):
-        pytest.skip("NRB_PATH_TC1 covers k <= 112 and d <= 256 (PATH_AUTO routes the rest to 3xTF32)")
+    if path in ("tc1", "tc16") and (k > 112 or d > 256):
+        pytest.skip("the filter paths cover k <= 112 and d <= 256 (PATH_AUTO routes the rest to 3xTF32)")
     rng = np.random.default_rng(nq * 1000 + nb + d + k)
     xb = rng.standard_normal((nb, d), dtype=np.float32)
     xq = rng.standard_normal((nq, d), dtype=np.float32)
@@ -72,7 +104,7 @@ def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
     assert rep["recall"] == 1.0 or rep["tie_exempt_queries"] > 0
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc1"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc1", "tc16"])
 def test_identity_duplicates_and_padding(nf, path):
     d = 32
     eye = np.eye(d, dtype=np.float32)
@@ -199,7 +231,8 @@ def test_tc_kernel_variants(nf, oracle, variant, metric):
         lib.nrb_set_tc_variant(2)
 
 
-def test_tc1_filter_margin_and_fallback(nf, oracle):
+@pytest.mark.parametrize("filt", ["tc1", "tc16"])
+def test_tc1_filter_margin_and_fallback(nf, oracle, filt):
     """The 1xTF32 filter: (a) on ordinary data no query needs the 3xTF32 fallback, i.e. every
     estimate stayed inside the assumed error bound and the margin set fitted its slots;
     (b) with hundreds of exact duplicates the margin set overflows, the queries are flagged,
@@ -210,7 +243,7 @@ def test_tc1_filter_margin_and_fallback(nf, oracle):
     xq = synth.user_profiles(xb, topics, 2000, 4)
     for metric in (0, 1):
         n0 = lib.nrb_fallback_query_count()
-        D, I = _search(nf, xb, xq, 50, metric, "tc1")
+        D, I = _search(nf, xb, xq, 50, metric, filt)
         assert lib.nrb_fallback_query_count() == n0, "fallback used on ordinary data"
         Do, Io = oracle.knn_fast(xq, xb, 50, metric)
         rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
@@ -220,7 +253,7 @@ def test_tc1_filter_margin_and_fallback(nf, oracle):
     xb = np.concatenate([np.repeat(base, 150, axis=0), rng.standard_normal((2000, 64), dtype=np.float32)])
     xq = base + 0.01 * rng.standard_normal((20, 64), dtype=np.float32)
     n0 = lib.nrb_fallback_query_count()
-    D, I = _search(nf, xb, xq, 10, 0, "tc1")
+    D, I = _search(nf, xb, xq, 10, 0, filt)
     assert lib.nrb_fallback_query_count() >= n0 + 20
     for q in range(20):
         assert len(set(I[q].tolist())) == 10 and (I[q] // 150 == q).all()  # ten of the 150 copies of base[q]
