@@ -149,73 +149,92 @@ __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float*
     }
 }
 
-// f[i] for a run-time i, as five levels of selects: a dynamically indexed register array would be
-// placed in local memory, and with 227 KB of the SM's 256 KB configured as shared memory nearly
-// every local access is an L2 round trip on the epilogue's critical path.
-__device__ __forceinline__ float pick32(const float (&f)[32], int i) {
-    float a[16], b[8], c[4];
-    const bool s4 = (i & 16) != 0, s3 = (i & 8) != 0, s2 = (i & 4) != 0, s1 = (i & 2) != 0, s0 = (i & 1) != 0;
+// 32 accumulator columns of the warp's 32 rows (thread = row): `v` holds the raw TMEM words of
+// columns [c0, c0 + 32) of this warpgroup's half. Keys above the row's threshold are appended to
+// the row's candidate buffer.
+//   * The common case is "nothing passes": instead of 32 compares, four 3-input max trees give
+//     the maxima of the four 8-column groups (16 FMNMX3/FMNMX), one more the chunk maximum, and a
+//     single compare + vote lets the warp skip the chunk.
+//   * Otherwise only the groups in which some lane has a hit are expanded, with STATIC register
+//     indices (predicated stores): a run-time index into the 32 keys would put them in local
+//     memory, and with 227 KB of the SM's 256 KB configured as shared memory nearly every local
+//     access is an L2 round trip on the epilogue's critical path.
+template <bool L2, bool FULL>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int valid, int id0, const float* nrm,
+                                          float m2inv, EpiRow& st, float* ck, int* ci, float* myk, int* myi,
+                                          int k, int keep_max, int lane) {
+    float f[32];
 #pragma unroll
-    for (int j = 0; j < 16; j++) a[j] = s4 ? f[16 + j] : f[j];
+    for (int i = 0; i < 32; i++) {
+        float x = __uint_as_float(v[i]);  // IP: stays in the accumulator's (scaled) domain
+        if (L2) x = -fmaxf(fmaf(x, m2inv, st.qn + nrm[c0 + i]), 0.f);
+        if (!FULL && c0 + i >= valid) x = NEG_INF;
+        f[i] = x;
+    }
+    float g[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) b[j] = s3 ? a[8 + j] : a[j];
+    for (int j = 0; j < 4; j++) {
+        const float* e = f + 8 * j;
+        g[j] = fmaxf(fmaxf(fmaxf(fmaxf(e[0], e[1]), e[2]), fmaxf(fmaxf(e[3], e[4]), e[5])), fmaxf(e[6], e[7]));
+    }
+    const float cmax = fmaxf(fmaxf(fmaxf(g[0], g[1]), g[2]), g[3]);
+    if (!__any_sync(0xffffffffu, cmax > st.cthr)) return;
+    const float ksc = L2 ? 1.f : st.inv;  // stored keys are always unscaled
 #pragma unroll
-    for (int j = 0; j < 4; j++) c[j] = s2 ? b[4 + j] : b[j];
-    const float d0 = s1 ? c[2] : c[0], d1 = s1 ? c[3] : c[1];
-    return s0 ? d1 : d0;
+    for (int j = 0; j < 4; j++) {
+        if (!__any_sync(0xffffffffu, g[j] > st.cthr)) continue;  // warp-uniform
+        if (g[j] > st.cthr) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (f[8 * j + i] > st.cthr) {
+                    myk[st.cnt] = f[8 * j + i] * ksc;
+                    myi[st.cnt] = id0 + c0 + 8 * j + i;
+                    st.cnt++;
+                }
+            }
+        }
+    }
+    // overflow guard (rare once the prune schedule is running): a chunk adds at most 32 entries
+    const unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
+    if (need) epi_prune_rows<L2>(need, st, ck, ci, k, keep_max, lane);
 }
 
-// One 128 x 256 accumulator: thread = query row, 8 chunks of 32 columns.
-//   taddr0  TMEM address of (this warp's lane quarter, accumulator column 0)
-//   valid   number of valid item columns in this tile (1..256)
-//   id0     item row index of column 0
-//   nrm     item norms of the tile in shared memory (L2 only)
+// One 128 x 256 accumulator, this warpgroup's 128 columns: four chunks of 32.
+//   taddr0  TMEM address of (this warp's lane quarter, first column of the warpgroup's half)
+//   valid   number of valid item columns in this half (FULL: all 128)
+//   id0     item row index of column 0 of the half
+//   nrm     item norms of the half in shared memory (L2 only)
 //   ck/ci   candidate buffers of this warp's 32 rows; myk/myi = this lane's row
+// FULL tiles software-pipeline the TMEM loads: the load of chunk c+1 is issued before chunk c is
+// processed, so its latency hides behind the selection work.
 template <bool L2, bool FULL>
 __device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
                                          float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                          int lane) {
     const float m2inv = -2.f * st.inv;
-#pragma unroll 1
-    for (int c0 = 0; c0 < HALF_N; c0 += 32) {  // taddr0 / id0 / nrm / valid are relative to the warpgroup's columns
-        if (!FULL && c0 >= valid) break;  // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
+    if (FULL) {
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32b_x32(taddr0, va);
         ptx::tmem_ld_wait();
-        // Branch-free pass mask (bit i: column c0+i beats the row's threshold).
-        float f[32];
-        uint32_t mask = 0;
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-            float x = __uint_as_float(v[i]);  // IP: stays in the accumulator's (scaled) domain
-            if (L2) x = -fmaxf(fmaf(x, m2inv, st.qn + nrm[c0 + i]), 0.f);
-            if (!FULL && c0 + i >= valid) x = NEG_INF;
-            f[i] = x;
-            mask |= (x > st.cthr) ? (1u << i) : 0u;
+        ptx::tmem_ld_32x32b_x32(taddr0 + 32, vb);
+        epi_chunk<L2, true>(va, 0, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(taddr0 + 64, va);
+        epi_chunk<L2, true>(vb, 32, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(taddr0 + 96, vb);
+        epi_chunk<L2, true>(va, 64, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
+        ptx::tmem_ld_wait();
+        epi_chunk<L2, true>(vb, 96, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
+    } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF_N; c0 += 32) {
+            if (c0 >= valid) break;  // warp-uniform
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
+            ptx::tmem_ld_wait();
+            epi_chunk<L2, false>(v, c0, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
         }
-        const float ksc = L2 ? 1.f : st.inv;  // stored keys are always unscaled
-        if (__all_sync(0xffffffffu, mask == 0xffffffffu)) {
-            // cold rows (first tile of a unit): everything passes, static indices
-            float* dk = myk + st.cnt;
-            int* di = myi + st.cnt;
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                dk[i] = f[i] * ksc;
-                di[i] = id0 + c0 + i;
-            }
-            st.cnt += 32;
-        } else if (mask) {
-            do {
-                const int i = __ffs(mask) - 1;
-                mask &= mask - 1;
-                myk[st.cnt] = pick32(f, i) * ksc;
-                myi[st.cnt] = id0 + c0 + i;
-                st.cnt++;
-            } while (mask);
-        }
-        // overflow guard (rare once the prune schedule below is running)
-        const unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
-        if (need) epi_prune_rows<L2>(need, st, ck, ci, k, keep_max, lane);
     }
 }
 
