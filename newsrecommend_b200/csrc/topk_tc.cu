@@ -46,7 +46,11 @@ constexpr int KC = 32;    // fp32 elements per K chunk (128-byte swizzle span)
 constexpr int A_BYTES = BM * KC * 4;        // 16 KB: 128 rows x 128 B
 constexpr int BH_BYTES = (BN / 2) * KC * 4; // 16 KB: half item tile (v2)
 constexpr int B_BYTES = BN * KC * 4;        // 32 KB: full item tile (v1)
-constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue warpgroups of 4 warps
+// Warps 0-3: control warpgroup (warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle); warps
+// 4-7 and 8-11: the two selection warpgroups. Roles are aligned to hardware warpgroups so that
+// setmaxnreg can move registers from the control warps to the selection warps.
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WGS = 2;
 constexpr int HALF_N = BN / EPI_WGS;  // columns of every tile handled by one warpgroup
 constexpr int TMEM_COLS = 512;
@@ -199,42 +203,25 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
     if (need) epi_prune_rows<L2>(need, st, ck, ci, k, keep_max, lane);
 }
 
-// One 128 x 256 accumulator, this warpgroup's 128 columns: four chunks of 32.
+// The ragged last tile of a unit (fewer than 128 valid columns in this warpgroup's half), chunk
+// by chunk.
 //   taddr0  TMEM address of (this warp's lane quarter, first column of the warpgroup's half)
-//   valid   number of valid item columns in this half (FULL: all 128)
+//   valid   number of valid item columns in this half
 //   id0     item row index of column 0 of the half
 //   nrm     item norms of the half in shared memory (L2 only)
 //   ck/ci   candidate buffers of this warp's 32 rows; myk/myi = this lane's row
-// FULL tiles software-pipeline the TMEM loads: the load of chunk c+1 is issued before chunk c is
-// processed, so its latency hides behind the selection work.
-template <bool L2, bool FULL>
-__device__ __forceinline__ void epi_tile(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
-                                         float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
-                                         int lane) {
+template <bool L2>
+__device__ __forceinline__ void epi_tile_ragged(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
+                                                float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
+                                                int lane) {
     const float m2inv = -2.f * st.inv;
-    if (FULL) {
-        uint32_t va[32], vb[32];
-        ptx::tmem_ld_32x32b_x32(taddr0, va);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x32(taddr0 + 32, vb);
-        epi_chunk<L2, true>(va, 0, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x32(taddr0 + 64, va);
-        epi_chunk<L2, true>(vb, 32, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x32(taddr0 + 96, vb);
-        epi_chunk<L2, true>(va, 64, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
-        ptx::tmem_ld_wait();
-        epi_chunk<L2, true>(vb, 96, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
-    } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < HALF_N; c0 += 32) {
-            if (c0 >= valid) break;  // warp-uniform
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
-            ptx::tmem_ld_wait();
-            epi_chunk<L2, false>(v, c0, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
-        }
+    for (int c0 = 0; c0 < HALF_N; c0 += 32) {
+        if (c0 >= valid) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
+        ptx::tmem_ld_wait();
+        epi_chunk<L2, false>(v, c0, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
     }
 }
 
@@ -302,10 +289,10 @@ template <bool L2, bool PAIR, bool NEED_QN>
 __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
                                              float (*nrm)[2][HALF_N], uint32_t tmem_base, int warp, int lane,
                                              uint32_t rank) {
-    const int wg = (warp - 2) >> 2;    // warpgroup = column half of every tile
+    const int wg = (warp - EPI_WARP0) >> 2;  // warpgroup = column half of every tile
     const int quad = warp & 3;         // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;  // query row inside the tile
-    const int etid = ((warp - 2) & 3) * 32 + lane;
+    const int etid = ((warp - EPI_WARP0) & 3) * 32 + lane;
     const int64_t crow0 = ((int64_t)blockIdx.x * EPI_WGS + wg) * BM + quad * 32;  // this warp's 32 buffer rows
     float* ck = A.cand_key_buf + crow0 * CAND_CAP;
     int* ci = A.cand_idx_buf + crow0 * CAND_CAP;
@@ -359,18 +346,40 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 st.cthr = L2 ? st.thr : st.thr * st.sc;
             }
             const uint32_t taddr0 = taddr_wg + (uint32_t)(acc * BN);
-            if (valid >= HALF_N)
-                epi_tile<L2, true>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            else if (valid > 0)
-                epi_tile<L2, false>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
-            // this warp's part of the accumulator is drained: hand it back to the MMA warp
-            ptx::tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (PAIR)
-                    ptx::mbar_arrive_cluster_relaxed(acc ? tempty_remote1 : tempty_remote0);
-                else
-                    ptx::mbar_arrive(&tempty[acc]);
+            // hands this warp's part of the accumulator back to the MMA warp
+            auto release = [&]() {
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR)
+                        ptx::mbar_arrive_cluster_relaxed(acc ? tempty_remote1 : tempty_remote0);
+                    else
+                        ptx::mbar_arrive(&tempty[acc]);
+                }
+            };
+            if (valid >= HALF_N) {
+                // Full tile: copy the warp's 32 x 128 scores into registers and give the accumulator
+                // back BEFORE selecting. The selection time of a tile varies from warp to warp (it
+                // depends on how many keys pass), and the MMA warp needs all 16 warps of the CTA
+                // pair to release an accumulator: releasing after the loads instead of after the
+                // selection lets the MMAs run a tile further ahead of the slowest warp.
+                uint32_t v0[32], v1[32], v2[32], v3[32];
+                ptx::tmem_ld_32x32b_x32(taddr0, v0);
+                ptx::tmem_ld_32x32b_x32(taddr0 + 32, v1);
+                ptx::tmem_ld_32x32b_x32(taddr0 + 64, v2);
+                ptx::tmem_ld_32x32b_x32(taddr0 + 96, v3);
+                ptx::tmem_ld_wait();
+                release();
+                const float m2inv = -2.f * st.inv;
+                const int id0 = un.b_row0 + col_base;
+                epi_chunk<L2, true>(v0, 0, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v1, 32, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v2, 64, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v3, 96, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
+            } else {
+                if (valid > 0)
+                    epi_tile_ragged<L2>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
+                release();
             }
             // Scheduled prune, after the accumulator went back: at tile counts 1, 2, 4, 8, ... every
             // warp of the CTA pair brings all of its rows back to their best k and tightens their
@@ -432,6 +441,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
+    if (warp < EPI_WARP0) ptx::setmaxnreg_dec<40>();
 
     // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow), and
     // only the instruction with side effects is issued by one elected lane: issued from divergent
@@ -509,8 +519,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else {
+    } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ selection epilogue
+        ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
                    cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, 0);
@@ -571,6 +582,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     ptx::cluster_sync_all();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
+    if (warp < EPI_WARP0) ptx::setmaxnreg_dec<40>();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -647,8 +659,9 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 }
             }
         }
-    } else {
+    } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
+        ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
                    cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
@@ -740,6 +753,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     ptx::cluster_sync_all();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
+    if (warp < EPI_WARP0) ptx::setmaxnreg_dec<40>();  // the CTA owns 12 warps x 168 registers; 4 x 40 + 8 x 232 = 12 x 168 exactly (a larger request never succeeds)
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -829,8 +843,9 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ filter epilogue (both CTAs)
+        ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
                    row_flags, cand_key_buf, cand_idx_buf, gthr, nullptr, 1, a_row_scale, b_scale};
         epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);

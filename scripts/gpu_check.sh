@@ -1,9 +1,9 @@
 #!/bin/bash
 # One gpurun call: the GPU parity suite, then the flat benchmark on both precision paths.
 # Usage (on the GPU box, from the repo root): bash scripts/gpu_check.sh [pytest -k expression]
-python -m pytest tests -m gpu -x -q ${1:+-k "$1"} > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tc1.json 2> gpurun_out/bench_err.log
-python bench.py --steps 10 --warmup 3 --path tc > gpurun_out/bench_tc.json 2>> gpurun_out/bench_err.log
+timeout 300 python -m pytest tests -m gpu -x -q ${1:+-k "$1"} > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
+timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tc1.json 2> gpurun_out/bench_err.log
+timeout 200 python bench.py --steps 10 --warmup 3 --path tc > gpurun_out/bench_tc.json 2>> gpurun_out/bench_err.log
 python - <<'PY'
 import json
 for f in ["bench_tc1", "bench_tc"]:
