@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libnrb200.so")
+# NRB_LIB selects another build of the same library (e.g. libnrb200_trace.so, `make trace`)
+LIB_PATH = os.environ.get("NRB_LIB") or os.path.join(_PKG, "libnrb200.so")
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1

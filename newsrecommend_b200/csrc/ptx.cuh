@@ -121,6 +121,11 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMa
         : "memory");
 }
 
+// Named barrier among `nthreads` threads of the CTA (whole warps).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Register reallocation between warpgroups (all four warps of a warpgroup execute it).
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {

@@ -60,6 +60,17 @@ constexpr int V1_STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 96 KB
 constexpr int V2_STAGES = 3;
 constexpr int V2_STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // 64 KB
 
+// Exchange area of the scheduled (pairwise) prune: the two selection warps that own the same 32
+// query rows -- one per warpgroup, i.e. per column half -- publish their rows' state here, split
+// the rows between them, and read the new state back.
+struct XchgShared {
+    int cnt[EPI_WGS][BM];    // in: the row's buffered entries per warpgroup; out: entries kept
+    float thr[EPI_WGS][BM];  // in: each warpgroup's append threshold for the row
+    float margin[BM];        // in: the row's error margin (filter kernels; else 0)
+    float nthr[BM];          // out: new append threshold (both warpgroups)
+    uint32_t lb[BM];         // out: ordered-uint lower bound of the row's k-th key (0: none yet)
+};
+
 template <int STAGES>
 struct TcShared {
     uint64_t full[STAGES];
@@ -69,10 +80,31 @@ struct TcShared {
     uint32_t tmem_base;
     uint32_t pad;
     float nrm[EPI_WGS][2][HALF_N];  // [warpgroup][tile parity]: staged item norms (L2)
+    XchgShared xchg;
 };
 
 constexpr size_t V1_SMEM = (size_t)V1_STAGES * V1_STAGE_BYTES + sizeof(TcShared<V1_STAGES>) + 1024;
 constexpr size_t V2_SMEM = (size_t)V2_STAGES * V2_STAGE_BYTES + sizeof(TcShared<V2_STAGES>) + 1024;
+
+// ---------------------------------------------------------------------------- timeline trace
+// Build with -DNRB_TRACE (make trace -> libnrb200_trace.so): cluster 0's leader CTA records
+// clock64() at the hand-off points of its first NRB_TRACE_TILES tiles; scripts/trace_timeline.py
+// reads it back with nrb_debug_trace_read and prints where each tile's time goes.
+#ifdef NRB_TRACE
+constexpr int NRB_TRACE_TILES = 4096;
+// [who][tile][event]: who 0 = MMA warp (0 tempty seen, 1 MMAs issued + committed),
+// who 1..8 = selection warps 4..11 (0 wait start, 1 tfull seen, 2 released, 3 tile done)
+__device__ long long g_trace[9][NRB_TRACE_TILES][4];
+#define NRB_TR(who, tile, ev)                                                                     \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < (uint32_t)NRB_TRACE_TILES)      \
+            g_trace[who][tile][ev] = clock64();                                                   \
+    } while (0)
+#else
+#define NRB_TR(who, tile, ev) \
+    do {                      \
+    } while (0)
+#endif
 
 // ---------------------------------------------------------------------------- epilogue
 struct EpiRow {
@@ -243,6 +275,154 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
     }
 }
 
+// Scheduled prune of 16 query rows by one warp, on the UNION of the two warpgroups' buffers of
+// each row (xs->cnt / thr / margin were published by both warps of the lane quarter):
+//   * a lower bound lb of the k-th best key of the union is found by bisection on the ordered-uint
+//     keys (count(key >= lb) in [k, k + 3], or exact after 32 halvings);
+//   * both buffers are compacted in place to their entries >= T = max(lb - margin, old thresholds)
+//     (everything dropped is below a valid bound of the row's k-th minus the margin);
+//   * T, lb and the new counts go back through xs.
+// Thresholds therefore follow the k-th best of ALL the row's columns although each warpgroup
+// keeps its own buffer, and the append rate per row is that of a single running top-k.
+// Two rows are processed together so that their loads and reduction chains overlap. Buffers
+// with more than 128 entries (possible only after heavy ties) are first brought down by the
+// single-buffer prune.
+constexpr int UT_SLACK = 3;
+__device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, int* ci_cta, int quad, int half,
+                                                int k, int keep_max) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+        int row[2], nA[2], nB[2];
+        float *kA[2], *kB[2];
+        int *iA[2], *iB[2];
+        float floor_t[2], mg[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            row[b] = quad * 32 + half * 16 + 2 * it + b;
+            kA[b] = ck_cta + (int64_t)row[b] * CAND_CAP;
+            iA[b] = ci_cta + (int64_t)row[b] * CAND_CAP;
+            kB[b] = kA[b] + (int64_t)BM * CAND_CAP;
+            iB[b] = iA[b] + (int64_t)BM * CAND_CAP;
+            nA[b] = xs->cnt[0][row[b]];
+            nB[b] = xs->cnt[1][row[b]];
+            mg[b] = xs->margin[row[b]];
+            floor_t[b] = fmaxf(xs->thr[0][row[b]], xs->thr[1][row[b]]);
+            // rare: a buffer beyond the 128-entry fast path is first pruned on its own
+            if (nA[b] > 128) {
+                const PruneOut o = tighten_row_call(kA[b], iA[b], nA[b], k, mg[b], keep_max, floor_t[b]);
+                nA[b] = o.kept;
+                floor_t[b] = fmaxf(floor_t[b], o.thr);
+                if (nA[b] > 128) {  // still too large (ties): exact prune to the best keep_max
+                    const PruneOut e = prune_row_call(kA[b], iA[b], nA[b], k, mg[b], keep_max, keep_max, kA[b], iA[b], floor_t[b]);
+                    nA[b] = e.kept;
+                    floor_t[b] = fmaxf(floor_t[b], e.thr);
+                }
+            }
+            if (nB[b] > 128) {
+                const PruneOut o = tighten_row_call(kB[b], iB[b], nB[b], k, mg[b], keep_max, floor_t[b]);
+                nB[b] = o.kept;
+                floor_t[b] = fmaxf(floor_t[b], o.thr);
+                if (nB[b] > 128) {
+                    const PruneOut e = prune_row_call(kB[b], iB[b], nB[b], k, mg[b], keep_max, keep_max, kB[b], iB[b], floor_t[b]);
+                    nB[b] = e.kept;
+                    floor_t[b] = fmaxf(floor_t[b], e.thr);
+                }
+            }
+        }
+        uint32_t u[2][8];
+        int id[2][8];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int e = i * 32 + lane;
+                const bool va = e < nA[b], vb = e < nB[b];
+                u[b][i] = va ? ordered_u32(kA[b][e]) : 0u;
+                id[b][i] = va ? iA[b][e] : -1;
+                u[b][4 + i] = vb ? ordered_u32(kB[b][e]) : 0u;
+                id[b][4 + i] = vb ? iB[b][e] : -1;
+            }
+        }
+        __syncwarp();
+        uint32_t lo[2], hi[2];
+        bool run[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                mn = (u[b][i] != 0u && u[b][i] < mn) ? u[b][i] : mn;
+                mx = u[b][i] > mx ? u[b][i] : mx;
+            }
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            run[b] = nA[b] + nB[b] >= k;
+            lo[b] = run[b] ? mn : 0u;  // invariant while running: count(u >= lo) >= k > count(u >= hi)
+            hi[b] = mx + 1u;
+            run[b] = run[b] && (hi[b] - lo[b] > 1u);
+        }
+        while (run[0] || run[1]) {  // warp-uniform
+            uint32_t mid[2];
+            int c[2];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                mid[b] = lo[b] + ((hi[b] - lo[b]) >> 1);
+                int cc = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) cc += (u[b][i] >= mid[b]) ? 1 : 0;
+                c[b] = cc;
+            }
+            c[0] = __reduce_add_sync(0xffffffffu, c[0]);
+            c[1] = __reduce_add_sync(0xffffffffu, c[1]);
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                if (run[b]) {
+                    if (c[b] >= k) {
+                        lo[b] = mid[b];
+                        if (c[b] <= k + UT_SLACK) run[b] = false;
+                    } else {
+                        hi[b] = mid[b];
+                    }
+                    if (hi[b] - lo[b] <= 1u) run[b] = false;
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const float thr = fmaxf(from_ordered_u32(lo[b]) - mg[b], floor_t[b]);  // lo == 0 -> NEG_INF
+            int baseA = 0, baseB = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float ka = from_ordered_u32(u[b][i]), kb = from_ordered_u32(u[b][4 + i]);
+                const bool keepa = (u[b][i] != 0u) && ka >= thr;
+                const bool keepb = (u[b][4 + i] != 0u) && kb >= thr;
+                const uint32_t ma = __ballot_sync(0xffffffffu, keepa), mb = __ballot_sync(0xffffffffu, keepb);
+                if (keepa) {
+                    const int pos = baseA + __popc(ma & lt);
+                    kA[b][pos] = ka;
+                    iA[b][pos] = id[b][i];
+                }
+                if (keepb) {
+                    const int pos = baseB + __popc(mb & lt);
+                    kB[b][pos] = kb;
+                    iB[b][pos] = id[b][4 + i];
+                }
+                baseA += __popc(ma);
+                baseB += __popc(mb);
+            }
+            if (lane == 0) {
+                xs->cnt[0][row[b]] = baseA;
+                xs->cnt[1][row[b]] = baseB;
+                xs->nthr[row[b]] = thr;
+                xs->lb[row[b]] = lo[b];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <bool L2>
 __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
                                                 int valid, int64_t b_total, int etid, int wg) {
@@ -287,8 +467,8 @@ struct EpiArgs {
 
 template <bool L2, bool PAIR, bool NEED_QN>
 __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
-                                             float (*nrm)[2][HALF_N], uint32_t tmem_base, int warp, int lane,
-                                             uint32_t rank) {
+                                             float (*nrm)[2][HALF_N], XchgShared* xs, uint32_t tmem_base, int warp,
+                                             int lane, uint32_t rank) {
     const int wg = (warp - EPI_WARP0) >> 2;  // warpgroup = column half of every tile
     const int quad = warp & 3;         // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;  // query row inside the tile
@@ -339,8 +519,10 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             // one still reads the current one (the named barrier keeps them within one tile)
             float* nrm_t = nrm[wg][acc];
             epi_stage_norms<L2>(nrm_t, A.b_norms, un, col_base, valid, A.b_total, etid, wg);
+            NRB_TR(warp - EPI_WARP0 + 1, gt, 0);
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
+            NRB_TR(warp - EPI_WARP0 + 1, gt, 1);
             if (st.gslot) {
                 st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
                 st.cthr = L2 ? st.thr : st.thr * st.sc;
@@ -370,6 +552,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 ptx::tmem_ld_32x32b_x32(taddr0 + 96, v3);
                 ptx::tmem_ld_wait();
                 release();
+                NRB_TR(warp - EPI_WARP0 + 1, gt, 2);
                 const float m2inv = -2.f * st.inv;
                 const int id0 = un.b_row0 + col_base;
                 epi_chunk<L2, true>(v0, 0, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
@@ -381,16 +564,27 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                     epi_tile_ragged<L2>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
                 release();
             }
-            // Scheduled prune, after the accumulator went back: at tile counts 1, 2, 4, 8, ... every
-            // warp of the CTA pair brings all of its rows back to their best k and tightens their
-            // thresholds. A row's pass rate is ~k/n after n items, so each doubling admits ~k new
-            // candidates per row: buffers stay near 2k entries (the 128-entry sort) and, because the
-            // 16 warps that share every accumulator hand-off prune in the SAME tiles, the hand-offs
-            // in between never wait for a straggler in the middle of a 256-entry sort.
+            // Scheduled prune: at tile counts 1, 2, 4, 8, ... every warp of the CTA pair brings its
+            // rows back to (about) their best k and tightens their thresholds. A row's pass rate is
+            // ~k/n after n items, so each doubling admits ~k new candidates per row; and because the 16
+            // warps that share every accumulator hand-off prune in the SAME tiles, the hand-offs in
+            // between never wait for one straggler. The two warps of a lane quarter (one per column
+            // half) do it together on the union of their buffers: see union_tighten_rows.
             const uint32_t tp = (uint32_t)t + 1u;
             if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles) {
-                const unsigned need = __ballot_sync(0xffffffffu, st.cnt > st.base);
-                if (need) epi_prune_rows<L2>(need, st, ck, ci, A.k, A.pw, lane);
+                xs->cnt[wg][row] = st.cnt;
+                xs->thr[wg][row] = st.thr;
+                if (wg == 0) xs->margin[row] = st.margin;
+                ptx::named_bar_sync(3 + quad, 64);
+                union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
+                                   A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw);
+                ptx::named_bar_sync(3 + quad, 64);
+                st.cnt = xs->cnt[wg][row];
+                st.base = st.cnt;
+                st.thr = xs->nthr[row];
+                st.cthr = L2 ? st.thr : st.thr * st.sc;
+                const uint32_t lbu = xs->lb[row];
+                if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
             }
         }
         epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
@@ -524,7 +718,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
                    cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
-        epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, 0);
+        epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, 0);
     }
 
     ptx::tcgen05_fence_before();
@@ -664,7 +858,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
                    cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
-        epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
+        epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
     ptx::tcgen05_fence_before();
@@ -686,13 +880,18 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 // true top-k. select_refine_kernel rescoring those <= k+32 candidates exactly in fp32 gives
 // the final order; rows with more candidates than slots are flagged and recomputed by the
 // 3xTF32 kernel.
-constexpr int V3_STAGES = 6;
-constexpr int V3_MAX_NKC = 8;
-constexpr int V3_A_BYTES = V3_MAX_NKC * A_BYTES;  // 128 KB resident query tile
+constexpr int V3_MAX_NKC = 8;  // tf32: kp <= 256 floats = 8 chunks of 128 bytes; fp16: 4 chunks
 
+template <bool F16>
+struct Tc3Cfg {
+    static constexpr int STAGES = F16 ? 8 : 5;                          // 16 KB item half-tile stages
+    static constexpr int A_TILE_BYTES = (F16 ? 4 : V3_MAX_NKC) * A_BYTES;  // resident query tile: 64 / 128 KB
+};
+
+template <int STAGES>
 struct Tc3Shared {
-    uint64_t full[V3_STAGES];
-    uint64_t empty[V3_STAGES];
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint64_t afull;
@@ -700,9 +899,14 @@ struct Tc3Shared {
     uint32_t tmem_base;
     uint32_t pad;
     float nrm[EPI_WGS][2][HALF_N];
+    XchgShared xchg;
 };
-constexpr size_t V3_SMEM = (size_t)V3_A_BYTES + (size_t)V3_STAGES * BH_BYTES + sizeof(Tc3Shared);  // no slack: __align__(1024)
-static_assert(V3_SMEM <= 232448, "topk_tc3_kernel exceeds the 227 KB of shared memory per CTA");
+template <bool F16>
+constexpr size_t v3_smem() {  // no slack: the dynamic shared memory is declared __align__(1024)
+    return (size_t)Tc3Cfg<F16>::A_TILE_BYTES + (size_t)Tc3Cfg<F16>::STAGES * BH_BYTES + sizeof(Tc3Shared<Tc3Cfg<F16>::STAGES>);
+}
+static_assert(v3_smem<false>() <= 232448 && v3_smem<true>() <= 232448,
+              "topk_tc3_kernel exceeds the 227 KB of shared memory per CTA");
 
 // F16: the operand planes are IEEE fp16 (same 11-bit significand as tf32, so the same error
 // bound) scaled by powers of two -- per row on the query side, one scale on the item side. K
@@ -716,13 +920,13 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 int64_t a_total, int64_t b_total, float* __restrict__ part_key, int* __restrict__ part_idx,
                 int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf,
                 unsigned* __restrict__ gthr, const float* __restrict__ a_row_scale, float b_scale) {
-    constexpr int STAGES = V3_STAGES;
+    constexpr int STAGES = Tc3Cfg<F16>::STAGES;
     constexpr int KE = F16 ? 2 * KC : KC;  // elements per 128-byte K chunk
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;  // 128-byte swizzled tiles need 1024-byte alignment
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* smem_b = smem + V3_A_BYTES;
-    Tc3Shared* sh = reinterpret_cast<Tc3Shared*>(smem_b + (size_t)STAGES * BH_BYTES);
+    uint8_t* smem_b = smem + Tc3Cfg<F16>::A_TILE_BYTES;
+    Tc3Shared<STAGES>* sh = reinterpret_cast<Tc3Shared<STAGES>*>(smem_b + (size_t)STAGES * BH_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -800,15 +1004,17 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             uint32_t phase = 0, a_phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            uint32_t mma_gt = 0;  // running tile index (trace builds)
             for (int p = cluster_id; p < n_pairs; p += n_clusters) {
                 const Unit un = units[2 * p];
                 const int ntiles = (un.b_rows + BN - 1) / BN;
                 ptx::mbar_wait(&sh->afull, a_phase);
                 ptx::tcgen05_fence_after();
                 a_phase ^= 1;
-                for (int t = 0; t < ntiles; t++) {
+                for (int t = 0; t < ntiles; t++, mma_gt++) {
                     ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
                     ptx::tcgen05_fence_after();
+                    NRB_TR(0, mma_gt, 0);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                     for (int kc = 0; kc < nkc; kc++) {
                         ptx::mbar_wait(&sh->full[stage], phase);
@@ -835,6 +1041,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                     }
                     if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);
                     __syncwarp();
+                    NRB_TR(0, mma_gt, 1);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -848,7 +1055,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
                    row_flags, cand_key_buf, cand_idx_buf, gthr, nullptr, 1, a_row_scale, b_scale};
-        epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, tmem_base, warp, lane, rank);
+        epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
     ptx::tcgen05_fence_before();
@@ -1046,8 +1253,8 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
 #define NRB_TC3_LAUNCH(L2V, F16V)                                                                                   \
     do {                                                                                                            \
         NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3_kernel<L2V, F16V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)V3_SMEM));                                                         \
-        topk_tc3_kernel<L2V, F16V><<<grid, NUM_THREADS, V3_SMEM, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw,      \
+                                            (int)v3_smem<F16V>()));                                                 \
+        topk_tc3_kernel<L2V, F16V><<<grid, NUM_THREADS, v3_smem<F16V>(), st>>>(mah, mbh, units, n_units_dev, nkc, k, pw,      \
                                                                       margin_scale, a->norms, b->norms, a->n, b->n, \
                                                                       part_key, part_idx, row_flags, ck, ci, gthr,  \
                                                                       ars, bsc);                                    \
@@ -1069,3 +1276,13 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
 }
 
 }  // namespace nrb
+
+#ifdef NRB_TRACE
+// Debug builds only (not part of include/nrb200.h): copies the timeline trace to the host.
+extern "C" int nrb_debug_trace_read(void* host_buf, size_t bytes) {
+    const size_t have = sizeof(long long) * 9 * nrb::NRB_TRACE_TILES * 4;
+    if (bytes < have) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    return cudaMemcpyFromSymbol(host_buf, nrb::g_trace, have) == cudaSuccess ? 0 : -2;
+}
+#endif
