@@ -570,6 +570,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             // warps that share every accumulator hand-off prune in the SAME tiles, the hand-offs in
             // between never wait for one straggler. The two warps of a lane quarter (one per column
             // half) do it together on the union of their buffers: see union_tighten_rows.
+            NRB_TR(warp - EPI_WARP0 + 1, gt, 3);
             const uint32_t tp = (uint32_t)t + 1u;
             if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles) {
                 xs->cnt[wg][row] = st.cnt;
