@@ -3,6 +3,7 @@
 // pieces of k-means.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -105,10 +106,12 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     if (p.tail_pairs > 0) {
         int max_split = nbt < 64 ? nbt : 64;
         // cost of a plan = waves x (chunk length + per-unit overhead), in catalogs per CTA pair;
-        // a unit costs about 16 tiles on top of its item rows (query-tile load, threshold
-        // warm-up, 32 final prunes per warp), which is what stops tiny batches from being cut
-        // into dozens of slivers
-        const double ov = 16.0 / nbt;
+        // a unit costs about 200 tiles of MMA time on top of its item rows (query-tile load, the
+        // append-heavy threshold warm-up and its prunes, 32 final sorts per warp; measured by
+        // sweeping NRB_FLAT_OV_TILES on config 1), which is what stops small batches from being
+        // cut into dozens of slivers
+        static const double ov_tiles = getenv("NRB_FLAT_OV_TILES") ? atof(getenv("NRB_FLAT_OV_TILES")) : 200.0;
+        const double ov = ov_tiles / nbt;
         double best_cost = 1e30;
         for (int s = 1; s <= max_split; s++) {
             const double waves = (double)(((int64_t)p.tail_pairs * s + C - 1) / C);

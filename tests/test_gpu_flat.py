@@ -259,3 +259,29 @@ def test_tc1_filter_margin_and_fallback(nf, oracle, filt):
         assert len(set(I[q].tolist())) == 10 and (I[q] // 150 == q).all()  # ten of the 150 copies of base[q]
     Do, Io = oracle.knn_fast(xq, xb, 10, 0)
     assert np.allclose(D, Do, rtol=1e-4)
+
+
+@pytest.mark.parametrize("path", ["tc16", "tc1", "tc"])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_adversarial_item_order(nf, oracle, path, metric):
+    """Worst case for a streaming top-k: the catalog is sorted so that every query's scores improve
+    monotonically along the scan (every item beats the running threshold: candidate buffers fill
+    up inside the tiles and the overflow guard has to prune over and over), and, separately, a
+    catalog sorted the other way (the first tile already holds the answer)."""
+    rng = np.random.default_rng(123)
+    d, nb, nq, k = 64, 30000, 200, 50
+    u = rng.standard_normal(d).astype(np.float32)
+    u /= np.linalg.norm(u)
+    xb = rng.standard_normal((nb, d), dtype=np.float32)
+    t = np.sort(rng.standard_normal(nb).astype(np.float32) * 4)  # strength along u, ascending
+    xb = xb - np.outer(xb @ u, u) + np.outer(t, u)
+    if metric == 1:
+        xq = 40.0 * u[None, :] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32)  # far along u: nearest = last rows
+    else:
+        xq = 3.0 * u[None, :] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32)
+    for order in (slice(None), slice(None, None, -1)):
+        xs = np.ascontiguousarray(xb[order])
+        D, I = _search(nf, xs, xq.astype(np.float32), k, metric, path)
+        Do, Io = oracle.knn_fast(xq.astype(np.float32), xs, k, metric)
+        rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xs) if metric == 1 else None)
+        assert rep["ok"], rep
