@@ -115,7 +115,8 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
     }
 }
 
-// Warp-cooperative prune of one row's candidate buffer. Sorts the first `n` entries of (bk, bi)
+// Warp-cooperative prune of one row's candidate buffer ((bk, bi) must have 32*R readable entries:
+// the candidate buffers always have CAND_CAP). Sorts the first `n` entries of (bk, bi)
 // best-first, finds kth = key of the k-th best (NEG_INF while fewer than k exist) and keeps the
 // best k PLUS every entry whose key is within `margin` of kth (key > kth - margin), at most
 // `keep_max`; writes `width` entries to (ok, oi) (kept ones, then empty candidates; ok/oi may
@@ -129,12 +130,18 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
                                                   int keep_max, int width, float* ok, int* oi, int lane,
                                                   int* kept, bool* overflow, float floor_thr = NEG_INF,
                                                   float* kth_out = nullptr) {
-    uint64_t c[R];
+    // unconditional loads (32*R <= CAND_CAP entries are always allocated; the tail is masked): the
+    // compiler batches them, whereas predicated loads were issued a few at a time
+    float rk[R];
+    int ri[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {
-        const int e = i * 32 + lane;
-        c[i] = (e < n) ? pack_cand(bk[e], bi[e]) : empty_cand();
+        rk[i] = bk[i * 32 + lane];
+        ri[i] = bi[i * 32 + lane];
     }
+    uint64_t c[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) c[i] = (i * 32 + lane < n) ? pack_cand(rk[i], ri[i]) : empty_cand();
     __syncwarp();
     warp_bitonic_desc<R>(c, lane);
     float kth = NEG_INF;
@@ -193,15 +200,16 @@ template <int R>
 __device__ __forceinline__ float warp_tighten_row(float* bk, int* bi, int n, int k, float margin, float floor_thr,
                                                   int lane, int* kept, uint32_t* lb_u) {
     constexpr int SLACK = 3;
-    uint32_t u[R];
+    float rk[R];
     int id[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        const int e = i * 32 + lane;
-        const bool valid = e < n;
-        u[i] = valid ? ordered_u32(bk[e]) : 0u;  // 0 sorts below every float
-        id[i] = valid ? bi[e] : -1;
+    for (int i = 0; i < R; i++) {  // unconditional, batched loads (see warp_prune_row_m)
+        rk[i] = bk[i * 32 + lane];
+        id[i] = bi[i * 32 + lane];
     }
+    uint32_t u[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) u[i] = (i * 32 + lane < n) ? ordered_u32(rk[i]) : 0u;  // 0 sorts below every float
     __syncwarp();
     uint32_t lo = 0;
     if (n >= k) {

@@ -95,6 +95,18 @@ constexpr int NRB_TRACE_TILES = 4096;
 // [who][tile][event]: who 0 = MMA warp (0 tempty seen, 1 MMAs issued + committed),
 // who 1..8 = selection warps 4..11 (0 wait start, 1 tfull seen, 2 released, 3 tile done)
 __device__ long long g_trace[9][NRB_TRACE_TILES][4];
+// scheduled prunes of the same warps: [who][prune #][0 publish, 1 partner arrived, 2 rows done, 3 partner done]
+__device__ long long g_trace_prune[9][64][4];
+__device__ int g_trace_prune_n[9];
+#define NRB_TRP(who, ev)                                                                                   \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_prune_n[who] < 64)                        \
+            g_trace_prune[who][g_trace_prune_n[who]][ev] = clock64();                                      \
+    } while (0)
+#define NRB_TRP_NEXT(who)                                                        \
+    do {                                                                         \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_trace_prune_n[who]++; \
+    } while (0)
 #define NRB_TR(who, tile, ev)                                                                     \
     do {                                                                                          \
         if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < (uint32_t)NRB_TRACE_TILES)      \
@@ -103,6 +115,12 @@ __device__ long long g_trace[9][NRB_TRACE_TILES][4];
 #else
 #define NRB_TR(who, tile, ev) \
     do {                      \
+    } while (0)
+#define NRB_TRP(who, ev) \
+    do {                 \
+    } while (0)
+#define NRB_TRP_NEXT(who) \
+    do {                  \
     } while (0)
 #endif
 
@@ -331,18 +349,30 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                 }
             }
         }
-        uint32_t u[2][8];
+        // All 32 loads are UNCONDITIONAL (entries beyond a buffer's count are inside its 256-entry
+        // allocation and are masked afterwards): predicated loads were issued a few at a time, each
+        // batch waiting for the previous one -- eight L2 round trips per row pair instead of one.
+        float rk[2][8];
         int id[2][8];
 #pragma unroll
         for (int b = 0; b < 2; b++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int e = i * 32 + lane;
-                const bool va = e < nA[b], vb = e < nB[b];
-                u[b][i] = va ? ordered_u32(kA[b][e]) : 0u;
-                id[b][i] = va ? iA[b][e] : -1;
-                u[b][4 + i] = vb ? ordered_u32(kB[b][e]) : 0u;
-                id[b][4 + i] = vb ? iB[b][e] : -1;
+                rk[b][i] = kA[b][e];
+                id[b][i] = iA[b][e];
+                rk[b][4 + i] = kB[b][e];
+                id[b][4 + i] = iB[b][e];
+            }
+        }
+        uint32_t u[2][8];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int e = i * 32 + lane;
+                u[b][i] = e < nA[b] ? ordered_u32(rk[b][i]) : 0u;
+                u[b][4 + i] = e < nB[b] ? ordered_u32(rk[b][4 + i]) : 0u;
             }
         }
         __syncwarp();
@@ -576,10 +606,15 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 xs->cnt[wg][row] = st.cnt;
                 xs->thr[wg][row] = st.thr;
                 if (wg == 0) xs->margin[row] = st.margin;
+                NRB_TRP(warp - EPI_WARP0 + 1, 0);
                 ptx::named_bar_sync(3 + quad, 64);
+                NRB_TRP(warp - EPI_WARP0 + 1, 1);
                 union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
                                    A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw);
+                NRB_TRP(warp - EPI_WARP0 + 1, 2);
                 ptx::named_bar_sync(3 + quad, 64);
+                NRB_TRP(warp - EPI_WARP0 + 1, 3);
+                NRB_TRP_NEXT(warp - EPI_WARP0 + 1);
                 st.cnt = xs->cnt[wg][row];
                 st.base = st.cnt;
                 st.thr = xs->nthr[row];
@@ -1285,5 +1320,16 @@ extern "C" int nrb_debug_trace_read(void* host_buf, size_t bytes) {
     if (bytes < have) return -1;
     if (cudaDeviceSynchronize() != cudaSuccess) return -2;
     return cudaMemcpyFromSymbol(host_buf, nrb::g_trace, have) == cudaSuccess ? 0 : -2;
+}
+extern "C" int nrb_debug_trace_prune_read(void* host_buf, size_t bytes, int reset) {
+    const size_t have = sizeof(long long) * 9 * 64 * 4;
+    if (bytes < have) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(host_buf, nrb::g_trace_prune, have) != cudaSuccess) return -2;
+    if (reset) {
+        int z[9] = {0};
+        cudaMemcpyToSymbol(nrb::g_trace_prune_n, z, sizeof(z));
+    }
+    return 0;
 }
 #endif

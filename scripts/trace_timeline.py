@@ -22,9 +22,12 @@ xq = synth.user_profiles(xb, topics, NQ, 43)
 idx = nf.IndexFlatIP(D)
 idx.add(xb)
 q = nf.PackedMatrix.from_tensor(torch.from_numpy(xq).cuda(), planes=idx._query_planes(K))
-for _ in range(2):
-    idx.search_packed(q, K)
+idx.search_packed(q, K)
+pb = np.zeros((9, 64, 4), dtype=np.int64)
+_lib.lib.nrb_debug_trace_prune_read(C.c_void_p(pb.ctypes.data), C.c_size_t(pb.nbytes), 1)  # reset the prune counters
+idx.search_packed(q, K)
 torch.cuda.synchronize()
+assert _lib.lib.nrb_debug_trace_prune_read(C.c_void_p(pb.ctypes.data), C.c_size_t(pb.nbytes), 0) == 0
 T = 4096
 buf = np.zeros((9, T, 4), dtype=np.int64)
 rc = _lib.lib.nrb_debug_trace_read(C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes))
@@ -64,6 +67,13 @@ for name, lo, hi in (("tiles 2-31", 2, 32), ("tiles 32-255", 32, 256), ("tiles 2
     r["tempty_seen_minus_last_local_release(t->t+2)"] = stats(mma[lo + 2:hi + 2, 0] - rel)
     r["tfull_seen_minus_mma_commit"] = stats(np.min(np.stack([e[lo:hi, 1] for e in epi]), axis=0) - mma[lo:hi, 1])
     out[name] = r
+# scheduled prunes of the first unit (11 of them): per warp, cycles waiting for the partner warp,
+# pruning its 16 rows, waiting for the partner to finish
+pr = pb[1:, :11, :]
+out["scheduled_prunes_first_unit"] = {
+    "wait_partner_in": stats(pr[:, :, 1] - pr[:, :, 0]), "prune_16_rows": stats(pr[:, :, 2] - pr[:, :, 1]),
+    "wait_partner_out": stats(pr[:, :, 3] - pr[:, :, 2]),
+    "prune_16_rows_by_prune_index_mean": [float(x) for x in (pr[:, :, 2] - pr[:, :, 1]).mean(axis=0)]}
 print(json.dumps(out, indent=1))
 json.dump(out, open("gpurun_out/trace_timeline.json", "w"), indent=1)
 np.save("gpurun_out/trace_raw.npy", buf[:, :3000])
