@@ -97,6 +97,30 @@ def _to_host_pair(D: torch.Tensor, I: torch.Tensor, Do=None, Io=None):
     return Do, Io
 
 
+_COPY_STREAMS: dict = {}
+
+
+def _copy_streams():
+    """(host-to-device, device-to-host) side streams of the current device."""
+    dev = torch.cuda.current_device()
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return _COPY_STREAMS[dev]
+
+
+_WAVE_ROWS: dict = {}
+
+
+def _wave_rows() -> int:
+    """Query rows of one full wave of the tcgen05 kernels: 256 per CTA pair."""
+    dev = torch.cuda.current_device()
+    if dev not in _WAVE_ROWS:
+        n = C.c_int(0)
+        ok = lib.nrb_device_info(C.byref(n), None, None) == 0 and n.value >= 2
+        _WAVE_ROWS[dev] = (n.value if ok else 148) // 2 * 256
+    return _WAVE_ROWS[dev]
+
+
 def _h16_scale_for(max_norm: float) -> float:
     """Power of two s with max_norm * s in [2^14, 2^15): no element of a row can overflow fp16."""
     if not (max_norm > 0.0) or not math.isfinite(max_norm):
@@ -265,16 +289,71 @@ class IndexFlat:
     def search(self, x, k: int, D=None, I=None):
         """(D, I) = search(x, k). Like faiss, optional preallocated numpy outputs D f32[nq,k],
         I i64[nq,k] are filled and returned (page-locked buffers avoid a staging copy)."""
-        t, from_np = _to_device_f32(x)
-        assert t.shape[1] == self.d
         assert k > 0
         if k > _lib.MAX_K:
             raise RuntimeError(f"k={k} > {_lib.MAX_K} is not supported by the selection stage")
+        if not isinstance(x, torch.Tensor) and torch.cuda.is_available():
+            a = np.ascontiguousarray(x, dtype=np.float32)
+            assert a.ndim == 2 and a.shape[1] == self.d
+            if a.shape[0] >= 2 * _wave_rows():
+                return self._search_host_pipelined(a, int(k), D, I)
+        t, from_np = _to_device_f32(x)
+        assert t.shape[1] == self.d
         q = PackedMatrix.from_tensor(t, planes=self._query_planes(int(k)))
         Dd, Id = self.search_packed(q, int(k))
         if from_np or D is not None or I is not None:
             return _to_host_pair(Dd, Id, D, I)
         return Dd, Id
+
+    def _search_host_pipelined(self, a: np.ndarray, k: int, D=None, I=None):
+        """Host arrays in, host arrays out, for batches of at least two waves: the batch is cut at
+        wave boundaries (one wave = one 256-query unit pair per CTA pair, so the cuts cost the
+        kernel nothing), all host-to-device copies are queued on a copy stream up front, and each
+        chunk's results travel back on a third stream while the next chunk is being searched."""
+        nq = a.shape[0]
+        dev = _device()
+        if D is None:
+            D = torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy()
+        if I is None:
+            I = torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy()
+        assert D.shape == (nq, k) and I.shape == (nq, k) and D.dtype == np.float32 and I.dtype == np.int64
+        assert D.flags.c_contiguous and I.flags.c_contiguous, "bad output array"
+        step = _wave_rows()
+        cuts = list(range(0, nq, step))
+        if len(cuts) > 1 and nq - cuts[-1] < step // 4:
+            cuts.pop()  # a sliver at the end rides with the previous chunk
+        bounds = [(lo, cuts[i + 1] if i + 1 < len(cuts) else nq) for i, lo in enumerate(cuts)]
+        cur = torch.cuda.current_stream()
+        h2d, d2h = _copy_streams()
+        h2d.wait_stream(cur)
+        src = torch.from_numpy(a)
+        staged, keep = [], []
+        with torch.cuda.stream(h2d):
+            for lo, hi in bounds:
+                xd = torch.empty((hi - lo, self.d), dtype=torch.float32, device=dev)
+                xd.copy_(src[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(h2d)
+                staged.append((xd, ev))
+        Dt, It = torch.from_numpy(D), torch.from_numpy(I)
+        planes = self._query_planes(k)
+        for (lo, hi), (xd, ev) in zip(bounds, staged):
+            cur.wait_event(ev)
+            xd.record_stream(cur)
+            q = PackedMatrix.from_tensor(xd, planes=planes)
+            Dd, Id = self.search_packed(q, k)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                Dt[lo:hi].copy_(Dd, non_blocking=True)
+                It[lo:hi].copy_(Id, non_blocking=True)
+            Dd.record_stream(d2h)
+            Id.record_stream(d2h)
+            keep.append((q, Dd, Id))
+        d2h.synchronize()
+        cur.wait_stream(d2h)
+        return D, I
 
     def _query_planes(self, k: int = 1):
         """Planes the chosen path reads on the query side (mirrors the eligibility rule of

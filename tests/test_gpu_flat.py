@@ -285,3 +285,25 @@ def test_adversarial_item_order(nf, oracle, path, metric):
         Do, Io = oracle.knn_fast(xq.astype(np.float32), xs, k, metric)
         rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xs) if metric == 1 else None)
         assert rep["ok"], rep
+
+
+def test_host_pipelined_search_matches_single_shot(nf):
+    """numpy in / numpy out with >= 2 waves of queries takes the chunked copy/compute pipeline:
+    same (D, I) as the packed single-shot search, with and without caller-provided outputs."""
+    import torch
+    rng = np.random.default_rng(31)
+    d, nb, k = 64, 4000, 10
+    nq = 2 * nf._wave_rows() + 1234
+    xb = rng.standard_normal((nb, d), dtype=np.float32)
+    xq = rng.standard_normal((nq, d), dtype=np.float32)
+    index = nf.IndexFlatIP(d)
+    index.add(xb)
+    q = nf.PackedMatrix.from_tensor(torch.from_numpy(xq).cuda(), planes=index._query_planes(k))
+    Dr, Ir = index.search_packed(q, k)
+    Dr, Ir = Dr.cpu().numpy(), Ir.cpu().numpy()
+    D1, I1 = index.search(xq, k)
+    assert np.array_equal(I1, Ir) and np.array_equal(D1, Dr)
+    Dp = torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy()
+    Ip = torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy()
+    D2, I2 = index.search(xq, k, D=Dp, I=Ip)
+    assert D2 is Dp and I2 is Ip and np.array_equal(I2, Ir) and np.array_equal(D2, Dr)
