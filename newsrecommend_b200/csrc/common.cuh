@@ -124,7 +124,8 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
 // is set when more than keep_max entries were within the margin (the row is then incomplete
 // and must be recomputed by the exact path). margin = 0, keep_max = width = k is the plain
 // top-k prune. All 32 lanes must call with identical arguments.
-// R = registers per lane: the sort covers 32*R entries, so n (and width) must be <= 32*R.
+// R = registers per lane: the sort covers 32*R entries, so n must be <= 32*R (width may be larger:
+// the rest of the output row is padding). When ok aliases bk, width must be <= 32*R.
 template <int R = CAND_CAP / 32>
 __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi, int n, int k, float margin,
                                                   int keep_max, int width, float* ok, int* oi, int lane,
@@ -183,6 +184,10 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
             ok[e] = keep ? cand_key(c[i]) : NEG_INF;
             oi[e] = keep ? cand_idx(c[i]) : -1;
         }
+    }
+    for (int e = 32 * R + lane; e < width; e += 32) {  // output wider than the sort: padding
+        ok[e] = NEG_INF;
+        oi[e] = -1;
     }
     __syncwarp();
     return fmaxf(thr, floor_thr);  // threshold for further appends

@@ -151,7 +151,26 @@ __device__ __noinline__ PruneOut prune_row_call(const float* bk, const int* bi, 
     const int lane = threadIdx.x & 31;
     PruneOut o;
     bool ovf;
-    if (n <= 128 && width <= 128)
+    // the sort is sized by the entries present: a row whose threshold was hot from the start (later
+    // lists of an IVF query, later chunks of a split catalog) ends its unit with a handful
+    if (n == 0) {  // nothing buffered (dead row, or nothing beat an already hot threshold): padding only
+        for (int e = lane; e < width; e += 32) {
+            ok[e] = NEG_INF;
+            oi[e] = -1;
+        }
+        __syncwarp();
+        o.thr = floor_thr;
+        o.kth = NEG_INF;
+        o.kept = 0;
+        o.ovf = 0;
+        return o;
+    }
+    const bool inplace = (ok == bk);  // in-place prunes must also cover the whole output width
+    if (n <= 32 && !inplace)
+        o.thr = warp_prune_row_m<1>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
+    else if (n <= 64 && !inplace)
+        o.thr = warp_prune_row_m<2>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
+    else if (n <= 128 && width <= 128)
         o.thr = warp_prune_row_m<4>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
     else
         o.thr = warp_prune_row_m<CAND_CAP / 32>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf,
