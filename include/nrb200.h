@@ -151,7 +151,11 @@ int nrb_ivf_build_lists(const int64_t* assign, int64_t n, int32_t nlist, int32_t
  * i64[lists->n] the external id of each packed row. Replaces Retrieval.py:32-34 in its
  * IndexIVFFlat form (north_star); results as nrb_search_flat. max_list_len = longest list
  * (host-known since add()). The (query, list) pairs are regrouped list-major on the device so
- * that every list is read once per 128 probing queries, not once per query. */
+ * that every list is read once per 128 probing queries, not once per query.
+ * path: NRB_PATH_SIMT, NRB_PATH_TC (3xTF32 scan), NRB_PATH_TC16 (fp16 filter over the lists with the
+ * proven margin + exact fp32 refine; needs raw, norms, h16 + scales and, for the queries the filter
+ * flags, hi / lo on both sides, lists->max_norm, kp <= 256, k <= 112) or NRB_PATH_AUTO (TC16 when
+ * those preconditions hold, else TC). TC16 synchronises the stream once per call. */
 size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k, int32_t kp, int32_t nlist,
                                 int32_t max_list_len);
 int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* offsets,

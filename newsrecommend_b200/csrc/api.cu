@@ -295,6 +295,9 @@ struct IvfWs {
     unsigned* gthr;
     Unit* units;
     float *g_raw, *g_hi, *g_lo, *g_norms, *part_key;
+    void* g_h16;     // fp16 filter: regrouped scaled fp16 query rows ...
+    float* g_scale;  // ... and their per-row scales
+    int *flags, *flag_list, *flag_count;
     int* part_idx;
     void* scratch;
     size_t scratch_bytes, total;
@@ -315,17 +318,26 @@ static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int
     w.src = c.take<int>((size_t)p.npairs * p.maxsplit * p.wgs);
     w.units = c.take<Unit>(p.max_units);
     const size_t plane = (size_t)(p.npairs + UNIT_ROWS) * kp;
+    const bool filt = path == NRB_PATH_TC16;
+    const int pw = filt ? tc1_pw(k) : k;  // partial row width
+    w.g_raw = w.g_hi = w.g_lo = w.g_scale = nullptr;
+    w.g_h16 = nullptr;
+    w.flags = w.flag_list = w.flag_count = nullptr;
     if (path == NRB_PATH_SIMT) {
         w.g_raw = c.take<float>(plane);
-        w.g_hi = w.g_lo = nullptr;
+    } else if (filt) {
+        w.g_h16 = c.take<uint16_t>(plane);
+        w.g_scale = c.take<float>(p.npairs + UNIT_ROWS);
+        w.flags = c.take<int>(nq);
+        w.flag_list = c.take<int>(nq);
+        w.flag_count = c.take<int>(1);
     } else {
-        w.g_raw = nullptr;
         w.g_hi = c.take<float>(plane);
         w.g_lo = c.take<float>(plane);
     }
     w.g_norms = c.take<float>(p.npairs + UNIT_ROWS);
-    w.part_key = c.take<float>((size_t)p.max_units * p.wgs * UNIT_ROWS * k);
-    w.part_idx = c.take<int>((size_t)p.max_units * p.wgs * UNIT_ROWS * k);
+    w.part_key = c.take<float>((size_t)p.max_units * p.wgs * UNIT_ROWS * pw);
+    w.part_idx = c.take<int>((size_t)p.max_units * p.wgs * UNIT_ROWS * pw);
     w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(p.grid) : tc_scratch_bytes(p.grid);
     w.scratch = c.take<char>(w.scratch_bytes);
     w.total = c.off;
@@ -456,11 +468,12 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     {
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
-                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, path == NRB_PATH_TC16, st);
+                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, nullptr, 1,
+                                 path == NRB_PATH_TC16, st);
     }
     if (rc) return rc;
     if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
-                                   id_base, w.flags, D, I, st))) return rc;
+                                   id_base, nullptr, w.flags, D, I, st))) return rc;
     if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
     int nflag = 0;
     NRB_CUDA_CHECK(cudaMemcpyAsync(&nflag, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -532,25 +545,33 @@ extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k
     IvfPlan p2 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_SIMT);
     size_t a = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC, nq).total;
     size_t b = carve_ivf(nullptr, p2, nlist, k, kp, NRB_PATH_SIMT, nq).total;
+    if (tc1_k_ok(k)) {
+        const size_t f = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC16, nq).total;
+        a = f > a ? f : a;
+    }
     return (a > b ? a : b) + 256;
 }
 
-extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* offsets,
-                              int32_t nlist, int32_t max_list_len, const int64_t* ids,
-                              const int64_t* coarse, int32_t nprobe, int32_t metric, int32_t k,
-                              float* D, int64_t* I, void* workspace, size_t workspace_bytes,
-                              int32_t path, void* stream) {
-    NRB_REQUIRE(q && lists && offsets && ids && coarse && D && I, "ivf_search: null argument");
-    NRB_REQUIRE(metric == NRB_METRIC_INNER_PRODUCT || metric == NRB_METRIC_L2, "ivf_search: bad metric %d", metric);
-    NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "ivf_search: k=%d out of range [1,%d]", k, NRB_MAX_K);
-    NRB_REQUIRE(nprobe >= 1 && nlist >= 1 && nlist <= 8192, "ivf_search: bad nprobe/nlist");
-    NRB_REQUIRE(q->d == lists->d && q->kp == lists->kp, "ivf_search: dimension mismatch");
-    NRB_REQUIRE(q->n * (int64_t)nprobe < (1LL << 31) - 4096 && lists->n < (1LL << 31) - 4096, "ivf_search: sizes out of range");
-    if (q->n == 0) return NRB_OK;
-    int rc = require_device();
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    path = resolve_path(path);  // the list scan runs 3xTF32 (or SIMT); the 1xTF32 filter is flat-only
+namespace nrb {
+
+// dst[i, :] = src[list[i], :] for rows of `width` 64-bit ids (coarse assignments of flagged queries)
+__global__ void gather_i64_rows_kernel(const int64_t* __restrict__ src, int width, const int* __restrict__ list,
+                                       int n, int64_t* __restrict__ dst) {
+    const int64_t total = (int64_t)n * width;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / width), j = (int)(t - (int64_t)i * width);
+        dst[t] = src[(int64_t)list[i] * width + j];
+    }
+}
+
+// path: NRB_PATH_SIMT, NRB_PATH_TC (3xTF32) or NRB_PATH_TC16 (fp16 filter + exact refine, flagged
+// queries recomputed through NRB_PATH_TC).
+static int ivf_search_impl(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* offsets, int nlist,
+                           int max_list_len, const int64_t* ids, const int64_t* coarse, int nprobe, int metric,
+                           int k, float* D, int64_t* I, void* workspace, size_t workspace_bytes, int path,
+                           cudaStream_t st) {
+    int rc;
+    const bool filt = path == NRB_PATH_TC16;
     const IvfPlan p = plan_ivf(q->n, nprobe, nlist, max_list_len, path);
     NRB_REQUIRE((int64_t)nprobe * p.maxsplit * p.wgs <= 256, "ivf_search: nprobe*splits = %d > 256 merge sources", nprobe * p.maxsplit * p.wgs);
     const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path, q->n);
@@ -573,43 +594,132 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     }
     // 3. query rows in group order
     nrb_matrix g;
+    memset(&g, 0, sizeof(g));
     g.n = p.npairs;
     g.d = q->d;
     g.kp = q->kp;
     g.raw = w.g_raw;
     g.hi = w.g_hi;
     g.lo = w.g_lo;
-    g.norms = nullptr;
     if (path == NRB_PATH_SIMT) {
         NRB_REQUIRE(q->raw, "ivf_search: raw plane required");
         if ((rc = launch_gather_rows(q->raw, q->kp, w.order, nprobe, p.npairs, w.g_raw, st))) return rc;
+    } else if (filt) {
+        // fp16 rows are kp/2 floats wide; their per-row scales and norms travel with them
+        if ((rc = launch_gather_rows((const float*)q->h16, q->kp / 2, w.order, nprobe, p.npairs, (float*)w.g_h16, st))) return rc;
+        if ((rc = launch_gather_scalar(q->h16_row_scale, w.order, nprobe, p.npairs, w.g_scale, st))) return rc;
+        g.h16 = w.g_h16;
+        g.h16_row_scale = w.g_scale;
     } else {
         NRB_REQUIRE(q->hi && q->lo, "ivf_search: hi/lo planes required");
         if ((rc = launch_gather_rows(q->hi, q->kp, w.order, nprobe, p.npairs, w.g_hi, st))) return rc;
         if ((rc = launch_gather_rows(q->lo, q->kp, w.order, nprobe, p.npairs, w.g_lo, st))) return rc;
     }
-    if (metric == NRB_METRIC_L2) {
-        NRB_REQUIRE(q->norms && lists->norms, "ivf_search: norms required for L2");
+    if (metric == NRB_METRIC_L2 || filt) {
+        NRB_REQUIRE(q->norms && lists->norms, "ivf_search: norms required");
         if ((rc = launch_gather_scalar(q->norms, w.order, nprobe, p.npairs, w.g_norms, st))) return rc;
         g.norms = w.g_norms;
     }
     // 4. distance + selection over the units, 5. merge per query
-    ProfScope prof(st);
-    if (path == NRB_PATH_SIMT)
-        rc = launch_topk_simt_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
-    else {
-        // all nprobe units of a query share one running bound: row p of the regrouped plane is
-        // pair order[p], i.e. query order[p] / nprobe
-        NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
-        rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch,
-                                w.scratch_bytes, w.gthr, w.order, nprobe, st);
+    const int S = nprobe * p.maxsplit * p.wgs;
+    if (path != NRB_PATH_SIMT) NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
+    if (!filt) {
+        {
+            ProfScope prof(st);
+            if (path == NRB_PATH_SIMT)
+                rc = launch_topk_simt_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
+            else
+                // all nprobe units of a query share one running bound: row p of the regrouped plane is
+                // pair order[p], i.e. query order[p] / nprobe
+                rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch,
+                                        w.scratch_bytes, w.gthr, w.order, nprobe, st);
+        }
+        if (rc) return rc;
+        return launch_select(w.part_key, w.part_idx, w.src, S, q->n, k, metric, ids, 0, D, I, st);
     }
-    if (prof.e1) {
-        cudaEventRecord(prof.e1, st);
-        prof.e1 = nullptr;
+    // ---- fp16 filter over the lists + exact refine, then 3xTF32 for whatever was flagged
+    const int pw = tc1_pw(k);
+    const float eps_xmax = TC1_EPS * lists->max_norm;
+    NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
+    {
+        ProfScope prof(st);
+        rc = launch_topk_tc1_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
+                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, w.order, nprobe, 1, st);
     }
     if (rc) return rc;
-    return launch_select(w.part_key, w.part_idx, w.src, nprobe * p.maxsplit * p.wgs, q->n, k, metric, ids, 0, D, I, st);
+    if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, S, q->n, k, pw, metric, q, lists, eps_xmax, 0, ids,
+                                   w.flags, D, I, st))) return rc;
+    if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
+    int nflag = 0;
+    NRB_CUDA_CHECK(cudaMemcpyAsync(&nflag, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NRB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (nflag == 0) return NRB_OK;
+    g_fallback_queries += nflag;
+    const size_t plane = (size_t)nflag * q->kp * sizeof(float);
+    const size_t wsb2 = nrb_ivf_search_workspace(nflag, nprobe, k, q->kp, nlist, max_list_len);
+    char* tmp = nullptr;
+    const size_t tmp_bytes = 2 * align_up(plane, 256) + align_up((size_t)nflag * 4, 256) +
+                             align_up((size_t)nflag * nprobe * 8, 256) + align_up((size_t)nflag * k * 4, 256) +
+                             align_up((size_t)nflag * k * 8, 256) + wsb2;
+    NRB_CUDA_CHECK(cudaMallocAsync((void**)&tmp, tmp_bytes, st));
+    Carver c(tmp);
+    float* fhi = c.take<float>((size_t)nflag * q->kp);
+    float* flo = c.take<float>((size_t)nflag * q->kp);
+    float* fnr = c.take<float>(nflag);
+    int64_t* fco = c.take<int64_t>((size_t)nflag * nprobe);
+    float* Df = c.take<float>((size_t)nflag * k);
+    int64_t* If = c.take<int64_t>((size_t)nflag * k);
+    void* ws2 = c.take<char>(wsb2);
+    rc = launch_gather_rows(q->hi, q->kp, w.flag_list, 1, nflag, fhi, st);
+    if (!rc) rc = launch_gather_rows(q->lo, q->kp, w.flag_list, 1, nflag, flo, st);
+    if (!rc) rc = launch_gather_scalar(q->norms, w.flag_list, 1, nflag, fnr, st);
+    if (!rc) {
+        gather_i64_rows_kernel<<<(unsigned)(((int64_t)nflag * nprobe + 255) / 256), 256, 0, st>>>(coarse, nprobe, w.flag_list, nflag, fco);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) rc = NRB_ERR_CUDA;
+    }
+    nrb_matrix qf = *q;
+    qf.raw = nullptr;
+    qf.h16 = nullptr;
+    qf.h16_row_scale = nullptr;
+    qf.hi = fhi;
+    qf.lo = flo;
+    qf.norms = fnr;
+    qf.n = nflag;
+    if (!rc) rc = ivf_search_impl(&qf, lists, offsets, nlist, max_list_len, ids, fco, nprobe, metric, k, Df, If, ws2, wsb2, NRB_PATH_TC, st);
+    if (!rc) rc = launch_scatter_results(Df, If, w.flag_list, nflag, k, D, I, st);
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+}  // namespace nrb
+
+extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, const int32_t* offsets,
+                              int32_t nlist, int32_t max_list_len, const int64_t* ids,
+                              const int64_t* coarse, int32_t nprobe, int32_t metric, int32_t k,
+                              float* D, int64_t* I, void* workspace, size_t workspace_bytes,
+                              int32_t path, void* stream) {
+    NRB_REQUIRE(q && lists && offsets && ids && coarse && D && I, "ivf_search: null argument");
+    NRB_REQUIRE(metric == NRB_METRIC_INNER_PRODUCT || metric == NRB_METRIC_L2, "ivf_search: bad metric %d", metric);
+    NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "ivf_search: k=%d out of range [1,%d]", k, NRB_MAX_K);
+    NRB_REQUIRE(nprobe >= 1 && nlist >= 1 && nlist <= 8192, "ivf_search: bad nprobe/nlist");
+    NRB_REQUIRE(q->d == lists->d && q->kp == lists->kp, "ivf_search: dimension mismatch");
+    NRB_REQUIRE(q->n * (int64_t)nprobe < (1LL << 31) - 4096 && lists->n < (1LL << 31) - 4096, "ivf_search: sizes out of range");
+    NRB_REQUIRE(path >= NRB_PATH_AUTO && path <= NRB_PATH_TC16 && path != NRB_PATH_TC1, "ivf_search: bad path %d", path);
+    if (q->n == 0) return NRB_OK;
+    int rc = require_device();
+    if (rc) return rc;
+    // the fp16 filter needs, besides its own planes, the raw planes (exact refine) and the hi/lo
+    // planes on both sides (flagged queries are recomputed by the 3xTF32 scan)
+    const bool filt_ok = tc16_eligible(q, lists, k) && q->hi && q->lo && lists->hi && lists->lo;
+    if (path == NRB_PATH_TC16 && !filt_ok) {
+        set_error("ivf_search: NRB_PATH_TC16 needs raw/h16/hi/lo/norms planes and h16 scales on both sides, "
+                  "max_norm on the list side, kp <= 256 and k <= %d", TC1_MAX_PW - TC1_MIN_EXTRA);
+        return NRB_ERR_INVALID;
+    }
+    if (path == NRB_PATH_AUTO) path = filt_ok ? NRB_PATH_TC16 : NRB_PATH_TC;
+    return ivf_search_impl(q, lists, offsets, nlist, max_list_len, ids, coarse, nprobe, metric, k, D, I, workspace,
+                           workspace_bytes, path, (cudaStream_t)stream);
 }
 
 extern "C" int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed) {

@@ -49,7 +49,8 @@ int tc16_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
-                        size_t scratch_bytes, unsigned* gthr, int f16, cudaStream_t st);
+                        size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
+                        cudaStream_t st);
 
 // ---- topk_simt.cu: fp32 CUDA-core distance + selection over the same Unit list
 size_t simt_scratch_bytes(int grid);
@@ -66,7 +67,7 @@ int launch_select(const float* part_key, const int* part_idx, const int* src, in
                   cudaStream_t st);
 int launch_select_refine(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
                          int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
-                         int64_t id_base, int* flags, float* D, int64_t* I, cudaStream_t st);
+                         int64_t id_base, const int64_t* id_map, int* flags, float* D, int64_t* I, cudaStream_t st);
 int launch_compact_flags(const int* flags, int64_t n, int* list, int* count, cudaStream_t st);
 int launch_scatter_results(const float* Df, const int64_t* If, const int* list, int n, int k, float* D,
                            int64_t* I, cudaStream_t st);

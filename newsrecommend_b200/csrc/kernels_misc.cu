@@ -409,8 +409,8 @@ template <int MAXL, bool L2>
 __global__ void select_refine_kernel(PartSource S, int64_t nq, int k, const float* __restrict__ q_raw,
                                      const float* __restrict__ q_norms, const float* __restrict__ b_raw,
                                      const float* __restrict__ b_norms, int kp, float eps_xmax,
-                                     int64_t id_base, int* __restrict__ flags, float* __restrict__ D,
-                                     int64_t* __restrict__ I) {
+                                     int64_t id_base, const int64_t* __restrict__ id_map, int* __restrict__ flags,
+                                     float* __restrict__ D, int64_t* __restrict__ I) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -485,7 +485,7 @@ __global__ void select_refine_kernel(PartSource S, int64_t nq, int k, const floa
                 I[q * k + r] = -1;
                 D[q * k + r] = L2 ? FLT_MAX : -FLT_MAX;
             } else {
-                I[q * k + r] = (int64_t)idx + id_base;
+                I[q * k + r] = id_map ? id_map[idx] : (int64_t)idx + id_base;
                 D[q * k + r] = L2 ? -key : key;
             }
         }
@@ -587,7 +587,7 @@ int launch_select(const float* part_key, const int* part_idx, const int* src, in
 
 int launch_select_refine(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
                          int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
-                         int64_t id_base, int* flags, float* D, int64_t* I, cudaStream_t st) {
+                         int64_t id_base, const int64_t* id_map, int* flags, float* D, int64_t* I, cudaStream_t st) {
     if (nq == 0) return NRB_OK;
     NRB_REQUIRE(S >= 1 && S <= 256 && pw <= 128 && k <= pw && q->kp <= 256, "select_refine: S=%d pw=%d kp=%d", S, pw, q->kp);
     PartSource ps{part_key, part_idx, src, S, pw};
@@ -598,11 +598,11 @@ int launch_select_refine(const float* part_key, const int* part_idx, const int* 
         if (metric == NRB_METRIC_L2)                                                                         \
             select_refine_kernel<MAXL, true><<<blocks, wpb * 32, 0, st>>>(ps, nq, k, q->raw, q->norms, b->raw, \
                                                                           b->norms, q->kp, eps_xmax, id_base, \
-                                                                          flags, D, I);                      \
+                                                                          id_map, flags, D, I);                      \
         else                                                                                                 \
             select_refine_kernel<MAXL, false><<<blocks, wpb * 32, 0, st>>>(ps, nq, k, q->raw, q->norms, b->raw, \
                                                                            b->norms, q->kp, eps_xmax, id_base, \
-                                                                           flags, D, I);                     \
+                                                                           id_map, flags, D, I);                     \
     } while (0)
     if (S <= 32)
         NRB_SR(1);

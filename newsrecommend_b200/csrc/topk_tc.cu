@@ -644,7 +644,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         }
         epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
                      A.part_idx, lane);
-        if (NEED_QN && st.flag && live) A.row_flags[ar] = 1;
+        if (NEED_QN && st.flag && live) A.row_flags[A.row_map ? A.row_map[ar] / A.row_div : (int)ar] = 1;  // per QUERY
     }
 }
 
@@ -974,7 +974,8 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 float margin_scale, const float* __restrict__ a_norms, const float* __restrict__ b_norms,
                 int64_t a_total, int64_t b_total, float* __restrict__ part_key, int* __restrict__ part_idx,
                 int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf,
-                unsigned* __restrict__ gthr, const float* __restrict__ a_row_scale, float b_scale) {
+                unsigned* __restrict__ gthr, const float* __restrict__ a_row_scale, float b_scale,
+                const int* __restrict__ row_map, int row_div) {
     constexpr int STAGES = Tc3Cfg<F16>::STAGES;
     constexpr int KE = F16 ? 2 * KC : KC;  // elements per 128-byte K chunk
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1109,7 +1110,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         // ------------------------------------------------------------------ filter epilogue (both CTAs)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   row_flags, cand_key_buf, cand_idx_buf, gthr, nullptr, 1, a_row_scale, b_scale};
+                   row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale};
         epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
@@ -1280,11 +1281,15 @@ int tc16_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
-                        size_t scratch_bytes, unsigned* gthr, int f16, cudaStream_t st) {
+                        size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
+                        cudaStream_t st) {
+    // what the KERNEL reads (the raw planes are the refine stage's business: *_eligible)
     if (f16)
-        NRB_REQUIRE(tc16_eligible(a, b, k), "tc16: not eligible (h16 planes + scales / raw / norms / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
+        NRB_REQUIRE(a->h16 && a->h16_row_scale && b->h16 && b->h16_scale > 0.f, "tc16: scaled fp16 planes required");
     else
-        NRB_REQUIRE(tc1_eligible(a, b, k), "tc1: not eligible (planes / kp <= 256 / k <= %d / max_norm)", TC1_MAX_PW - TC1_MIN_EXTRA);
+        NRB_REQUIRE(a->hi && b->hi, "tc1: hi planes required");
+    NRB_REQUIRE(a->norms && b->norms && a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && tc1_k_ok(k) && row_div >= 1,
+                "tc1: norms on both sides, kp <= 256 and k <= %d required", TC1_MAX_PW - TC1_MIN_EXTRA);
     NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - HALF_N, "tc1: bad kp / pw");
     NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
     if (scratch_bytes < tc_scratch_bytes(grid)) {
@@ -1312,7 +1317,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
         topk_tc3_kernel<L2V, F16V><<<grid, NUM_THREADS, v3_smem<F16V>(), st>>>(mah, mbh, units, n_units_dev, nkc, k, pw,      \
                                                                       margin_scale, a->norms, b->norms, a->n, b->n, \
                                                                       part_key, part_idx, row_flags, ck, ci, gthr,  \
-                                                                      ars, bsc);                                    \
+                                                                      ars, bsc, row_map, row_div);                  \
     } while (0)
     if (metric == NRB_METRIC_L2) {
         if (f16)

@@ -621,6 +621,15 @@ class IndexIVFFlat:
         check(lib.nrb_pack_rows(raw.data_ptr(), n, self.d, kp, kp, 0, packed.hi.data_ptr(), packed.lo.data_ptr(),
                                 packed.norms.data_ptr(), _stream()), "pack_rows")
         packed.n = n
+        # scaled fp16 plane + max norm: the fp16 filter of the list scan (NRB_PATH_TC16)
+        if n:
+            packed.track_max_norm = True
+            packed.max_norm = float(packed.norms[:n].max().sqrt())
+            if packed.max_norm > 0.0:
+                packed.h16 = torch.empty((n, kp), dtype=torch.float16, device=dev)
+                packed.h16_scale = _h16_scale_for(packed.max_norm)
+                check(lib.nrb_pack_rows_h16(raw.data_ptr(), n, self.d, kp, kp, packed.h16_scale,
+                                            packed.h16.data_ptr(), 0, _stream()), "pack_rows_h16")
         ids = order[:n].to(torch.int64)  # ids are sequential: id = insertion row
         off_h = _to_host(offsets).astype(np.int64)
         sizes = np.diff(off_h)
@@ -648,8 +657,13 @@ class IndexIVFFlat:
             I.fill_(-1)
         elif nq:
             L = self._build_lists()
+            # PATH_AUTO: fp16 filter + exact refine over the lists when eligible (raw, norms, h16 for
+            # the filter; hi, lo for the queries it flags), else the 3xTF32 scan
+            filt = self.path in (PATH_AUTO, PATH_TC16) and L["packed"].h16 is not None and k <= 112 and \
+                _round_kp(self.d) <= 256
             planes = ("raw",) if self.path == PATH_SIMT else ("hi", "lo")
             planes = tuple(dict.fromkeys(planes + self.quantizer._query_planes(nprobe) +
+                                         (("raw", "norms", "h16") if filt else ()) +
                                          (("norms",) if self.metric_type == METRIC_L2 else ())))
             ls = L["packed"].struct()
             for q0 in range(0, nq, IVF_QUERY_BATCH):

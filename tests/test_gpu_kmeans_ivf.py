@@ -129,7 +129,7 @@ def _same_centroids_ivf(nf, oracle, xb, nlist, metric, path):
     return ivf_g, ivf_o
 
 
-@pytest.mark.parametrize("path", [2, 1])
+@pytest.mark.parametrize("path", [4, 2, 1, 0])  # fp16 filter + refine, 3xTF32, SIMT, auto
 @pytest.mark.parametrize("metric", [0, 1])
 def test_ivf_search_against_oracle(nf, oracle, metric, path):
     from newsrecommend_b200 import synth
@@ -191,3 +191,25 @@ def test_ivf_end_to_end_train_quality(nf, oracle):
     assert sz_g.sum() == 80000 and sz_g.min() > 1
     r_g, r_o = recall_at_k(res[0][1], If), recall_at_k(res[1][1], If)
     assert abs(r_g - r_o) < 0.03 and r_g > 0.5, (r_g, r_o)
+
+
+def test_ivf_filter_fallback_on_duplicates(nf, oracle):
+    """The list scan's fp16 filter with hundreds of exact duplicates in one list: the margin sets
+    overflow, the queries are flagged and recomputed by the 3xTF32 scan; still a valid top-k."""
+    from newsrecommend_b200._lib import lib
+    rng = np.random.default_rng(17)
+    base = rng.standard_normal((20, 64), dtype=np.float32)
+    xb = np.concatenate([np.repeat(base, 150, axis=0), rng.standard_normal((3000, 64), dtype=np.float32)])
+    xq = base + 0.01 * rng.standard_normal((20, 64)).astype(np.float32)
+    ivf = nf.IndexIVFFlat(nf.IndexFlatIP(64), 64, 8, nf.METRIC_INNER_PRODUCT)
+    ivf.path = 4
+    ivf.train(xb)
+    ivf.add(xb)
+    ivf.nprobe = 8  # = nlist: exact
+    n0 = lib.nrb_fallback_query_count()
+    D, I = ivf.search(xq, 10)
+    assert lib.nrb_fallback_query_count() >= n0 + 20
+    for q in range(20):
+        assert len(set(I[q].tolist())) == 10 and (I[q] // 150 == q).all()
+    Do, Io = oracle.knn_fast(xq, xb, 10, 0)
+    assert np.allclose(D, Do, rtol=1e-4)
