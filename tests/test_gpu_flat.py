@@ -90,6 +90,7 @@ def test_golden_fixture(nf, path, metric):
     (1, 5000, 250, 50), (19, 5000, 250, 50), (20, 5000, 256, 50), (129, 3001, 250, 20),
     (300, 255, 64, 1), (300, 256, 64, 16), (257, 257, 3, 5), (64, 1000, 1, 10), (33, 2000, 257, 100),
     (130, 7, 12, 10), (5, 1, 40, 3), (1000, 20000, 250, 128),
+    (70, 3000, 96, 20), (300, 5000, 160, 50),  # fp16 rows of 192 / 320 bytes: the last 128-byte K chunk is zero-filled by TMA
 ])
 def test_shapes_against_oracle(nf, oracle, path, metric, nq, nb, d, k):
     if path in ("tc1", "tc16") and (k > 112 or d > 256):
@@ -307,3 +308,27 @@ def test_host_pipelined_search_matches_single_shot(nf):
     Ip = torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy()
     D2, I2 = index.search(xq, k, D=Dp, I=Ip)
     assert D2 is Dp and I2 is Ip and np.array_equal(I2, Ir) and np.array_equal(D2, Dr)
+
+
+def test_growing_norms_repack_fp16_plane(nf, oracle):
+    """add() of rows 1000x larger than the first batch outgrows the fp16 plane's scale: the plane is
+    re-packed from the raw plane and the search still matches the oracle on the whole catalog."""
+    rng = np.random.default_rng(55)
+    x1 = rng.standard_normal((3000, 128), dtype=np.float32)
+    x2 = rng.standard_normal((3000, 128), dtype=np.float32) * np.float32(1000.0)
+    xq = rng.standard_normal((200, 128), dtype=np.float32)
+    for metric in (0, 1):
+        index = nf.IndexFlatIP(128) if metric == 0 else nf.IndexFlatL2(128)
+        index.path = PATHS["tc16"]
+        index.add(x1)
+        s1 = index._xb.h16_scale
+        D, I = index.search(xq, 20)
+        Do, Io = oracle.knn_fast(xq, x1, 20, metric)
+        assert compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, x1) if metric == 1 else None)["ok"]
+        index.add(x2)
+        assert index._xb.h16_scale < s1
+        xb = np.concatenate([x1, x2])
+        D, I = index.search(xq, 20)
+        Do, Io = oracle.knn_fast(xq, xb, 20, metric)
+        rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
+        assert rep["ok"], rep
