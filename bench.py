@@ -360,12 +360,14 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "k": K,
                        "parallelism": ("single GPU" if world == 1 else
-                                       (f"queries split over {world} GPUs, packed catalog (1.1 GB) replicated, no data-path collective"
+                                       (f"queries split over {world} GPUs, packed catalog (1.3 GB) replicated, no data-path collective"
                                         if main_mode == "queries" else
                                         f"catalog row-sharded over {world} GPUs, NCCL all-gather + K4 merge")),
-                       "l2": "inputs larger than L2 (catalog hi+lo planes 746 MB per full catalog)",
+                       "l2": ("inputs larger than L2 (the kernel streams the 186 MB fp16 catalog plane, the refine gathers "
+                              "from the 373 MB fp32 plane; L2 is 126 MB)" if f16 else
+                              "inputs larger than L2 (catalog hi+lo planes 746 MB per full catalog)"),
                        "path": args.path, "fallback_queries": int(_lib.lib.nrb_fallback_query_count()),
-                       "timed": "K0 query split + K2 tcgen05 distance/selection + select" + (" + exact refine" if one_pass else "") +
+                       "timed": "K0 query pack + K2 tcgen05 distance/selection + select" + (" + exact refine" if one_pass else "") +
                                 (" + NCCL all-gather + K4 merge" if (world > 1 and main_mode == "catalog") else "")},
             "roofline": roof,
             "e2e": {"value": NQ * args.steps / e2e_s, "unit": "queries/s",

@@ -12,6 +12,8 @@ timeout 500 ncu --set full --clock-control none --import-source on -k regex:topk
 timeout 400 python scripts/bench_configs.py 4 5 > $O/ev_configs45.json 2>> $O/ev_err.log
 timeout 400 python scripts/bench_ivf.py > $O/ev_ivf.json 2>> $O/ev_err.log
 timeout 400 python scripts/bench_stage.py > $O/ev_stage.json 2>> $O/ev_err.log
+NRB_LIB=$PWD/newsrecommend_b200/libnrb200_trace.so timeout 300 python scripts/trace_timeline.py > $O/ev_trace.log 2>&1
+timeout 300 python -m pytest tests -m gpu -q > $O/ev_tests.log 2>&1; tail -2 $O/ev_tests.log
 tail -3 $O/ev_err.log
 python - <<'PY'
 import json
