@@ -339,10 +339,10 @@ def run_ours(args):
             "kernel_ms_avg": kavg_s * 1e3, "kernel_launches_timed": kern_n,
             "alg_flop_per_launch": alg,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at N = 1
-            # (ncu --set full; fp16 filter: profiles/r01_ncu_full_tc16_fp16_filter.csv, 0.72 GB + 0.21 GB;
+            # (ncu --set full; fp16 filter: profiles/r01_ncu_full_tc16_fp16_filter.csv, 0.86 GB + 0.22 GB;
             # tf32 filter: profiles/r01_ncu_full_tc3_final.csv, 7.53 GB + 1.22 GB); the
             # 3xTF32 kernel was captured before the last planner change (profiles/r01_ncu_full_prof_tc2.csv)
-            "traffic": (0.93e9 if f16 else 8.75e9 if one_pass else 50.2e9) if world == 1 else None,
+            "traffic": (1.08e9 if f16 else 8.75e9 if one_pass else 50.2e9) if world == 1 else None,
         }
         # correctness spot check inside the bench: a query sample against the oracle
         from oracle import faiss_oracle as fo
