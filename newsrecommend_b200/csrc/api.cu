@@ -86,6 +86,7 @@ struct FlatPlan {
     int wgs;         // epilogue warpgroups writing partial rows (2 for the tcgen05 kernels)
     int S;           // source slots per query = tsplit * wgs
     int grid;
+    int single;      // 1: single-CTA units (fp16 filter, one partial wave): unit c*nqt + t, no phantoms
 };
 
 static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
@@ -122,12 +123,41 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
             }
         }
     }
+    p.single = 0;
+    // One partial wave of the fp16 filter: single-CTA units (one query tile each, no phantom
+    // tile, 148 slots instead of 74) can sometimes be cut one step finer than CTA pairs, e.g.
+    // 49 tiles x 3 chunks = 147 units where 25 pairs stop at 2 chunks. CTA pairs halve the L2
+    // traffic per unit of work, so they stay unless the single-CTA plan is clearly shorter.
+    if (path == NRB_PATH_TC16 && p.full_pairs == 0 && p.nqt <= sm_count() && !getenv("NRB_NO_SINGLE_CTA")) {
+        const int C1 = sm_count();
+        static const double ov_tiles1 = getenv("NRB_FLAT_OV_TILES") ? atof(getenv("NRB_FLAT_OV_TILES")) : 200.0;
+        const double ov = ov_tiles1 / nbt;
+        const int max_split = nbt < 64 ? nbt : 64;
+        const double pair_cost = (double)(((int64_t)p.tail_pairs * best + C - 1) / C) * (1.0 / best + ov);
+        int best1 = 1;
+        double best_cost1 = 1e30;
+        for (int s = 1; s <= max_split; s++) {
+            const double waves = (double)(((int64_t)p.nqt * s + C1 - 1) / C1);
+            const double cost = waves * (1.0 / s + ov);
+            if (cost < best_cost1 * 0.97) {
+                best_cost1 = cost;
+                best1 = s;
+            }
+        }
+        if (best_cost1 < 0.9 * pair_cost || getenv("NRB_FORCE_SINGLE_CTA")) {  // (the override is for tests)
+            p.single = 1;
+            best = best1;
+        }
+    }
     const int tiles_per = (nbt + best - 1) / best;
     p.chunk_rows = tiles_per * tile;
     p.tsplit = (nbt + tiles_per - 1) / tiles_per;
-    p.n_units = 2 * (p.full_pairs + p.tail_pairs * p.tsplit);
+    p.n_units = p.single ? p.nqt * p.tsplit : 2 * (p.full_pairs + p.tail_pairs * p.tsplit);
     p.S = p.tsplit * p.wgs;
-    p.grid = simt ? simt_grid(p.n_units) : tc_grid(p.n_units);
+    if (p.single)
+        p.grid = p.n_units < sm_count() ? p.n_units : sm_count();
+    else
+        p.grid = simt ? simt_grid(p.n_units) : tc_grid(p.n_units);
     return p;
 }
 
@@ -411,8 +441,8 @@ extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, i
     if (nq <= 0 || k <= 0 || k > NRB_MAX_K) return 256;
     // take the largest over the paths so that `path` can be chosen per call
     size_t best = 0;
-    for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC1}) {  // TC16 carves like TC1
-        if (path == NRB_PATH_TC1 && !tc1_k_ok(k)) continue;
+    for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC1, NRB_PATH_TC16}) {
+        if ((path == NRB_PATH_TC1 || path == NRB_PATH_TC16) && !tc1_k_ok(k)) continue;
         FlatPlan p = plan_flat(nq, nb, k, path);
         size_t t = carve_flat(nullptr, p, nq, k, path).total;
         best = t > best ? t : best;
@@ -446,8 +476,12 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         return NRB_ERR_WORKSPACE;
     }
     int rc;
-    if ((rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.full_pairs, p.tail_pairs,
-                                     p.tsplit, p.chunk_rows, p.wgs, st))) return rc;
+    if (p.single)
+        rc = launch_fill_flat_units_single(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.tsplit, p.chunk_rows, p.wgs, st);
+    else
+        rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.full_pairs, p.tail_pairs, p.tsplit,
+                                    p.chunk_rows, p.wgs, st);
+    if (rc) return rc;
     if (w.gthr) NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
     if (!filt) {
         {
@@ -469,7 +503,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
                                  w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, nullptr, 1,
-                                 path == NRB_PATH_TC16, st);
+                                 path == NRB_PATH_TC16, p.single, st);
     }
     if (rc) return rc;
     if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
@@ -644,7 +678,7 @@ static int ivf_search_impl(const nrb_matrix* q, const nrb_matrix* lists, const i
     {
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
-                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, w.order, nprobe, 1, st);
+                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, w.order, nprobe, 1, 0, st);
     }
     if (rc) return rc;
     if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, S, q->n, k, pw, metric, q, lists, eps_xmax, 0, ids,

@@ -50,7 +50,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
-                        cudaStream_t st);
+                        int single, cudaStream_t st);
 
 // ---- topk_simt.cu: fp32 CUDA-core distance + selection over the same Unit list
 size_t simt_scratch_bytes(int grid);
@@ -73,6 +73,9 @@ int launch_scatter_results(const float* Df, const int64_t* If, const int* list, 
                            int64_t* I, cudaStream_t st);
 int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
                            int full_pairs, int tail_pairs, int tsplit, int chunk_rows, int wgs, cudaStream_t st);
+// single-CTA plan: unit c*nqt + t = query tile t against item chunk c (no phantom units)
+int launch_fill_flat_units_single(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
+                                  int tsplit, int chunk_rows, int wgs, cudaStream_t st);
 size_t counting_sort_ws(int64_t n, int nb);
 int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets, int* order,
                              int* pos_of, void* ws, size_t ws_bytes, cudaStream_t st);

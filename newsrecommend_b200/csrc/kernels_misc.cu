@@ -564,6 +564,35 @@ __global__ void fill_flat_units_kernel(Unit* __restrict__ units, int* __restrict
     }
 }
 
+// Single-CTA plan of the flat search: unit c*nqt + t = query tile t against item chunk c.
+__global__ void fill_flat_units_single_kernel(Unit* __restrict__ units, int* __restrict__ n_units_out,
+                                              int* __restrict__ src, int64_t nq, int64_t nb, int nqt, int tsplit,
+                                              int chunk_rows, int wgs) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nunits = (int64_t)nqt * tsplit;
+    if (tid == 0) *n_units_out = (int)nunits;
+    if (tid < nunits) {
+        const int c = (int)(tid / nqt), t = (int)(tid - (int64_t)c * nqt);
+        Unit u;
+        const int64_t ar = nq - (int64_t)t * UNIT_ROWS;
+        u.a_rows = (int)(ar < UNIT_ROWS ? ar : UNIT_ROWS);
+        u.a_row0 = t * UNIT_ROWS;
+        u.b_row0 = c * chunk_rows;
+        const int64_t br = nb - (int64_t)c * chunk_rows;
+        u.b_rows = (int)(br < chunk_rows ? (br > 0 ? br : 0) : chunk_rows);
+        units[tid] = u;
+    }
+    const int S = tsplit * wgs;
+    const int64_t total = nq * S;
+    for (int64_t e = tid; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = e / S;
+        const int sl = (int)(e - q * S);
+        const int c = sl / wgs, g = sl - c * wgs;
+        const int64_t u = (int64_t)c * nqt + q / UNIT_ROWS;
+        src[e] = (int)((u * wgs + g) * UNIT_ROWS + q % UNIT_ROWS);
+    }
+}
+
 // ------------------------------------------------------------------- host launchers
 int launch_select(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
                   int k, int metric, const int64_t* id_map, int64_t id_base, float* D, int64_t* I,
@@ -647,6 +676,20 @@ int launch_fill_flat_units(Unit* units, int* n_units_out, int* src, int64_t nq, 
     if (blocks < 1) blocks = 1;
     fill_flat_units_kernel<<<(unsigned)blocks, 256, 0, st>>>(units, n_units_out, src, nq, nb, nqt, full_pairs,
                                                              tail_pairs, tsplit, chunk_rows, wgs);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_fill_flat_units_single(Unit* units, int* n_units_out, int* src, int64_t nq, int64_t nb, int nqt,
+                                  int tsplit, int chunk_rows, int wgs, cudaStream_t st) {
+    const int64_t total = nq * tsplit * wgs;
+    const int64_t nunits = (int64_t)nqt * tsplit;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < (nunits + 255) / 256) blocks = (nunits + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    fill_flat_units_single_kernel<<<(unsigned)blocks, 256, 0, st>>>(units, n_units_out, src, nq, nb, nqt, tsplit,
+                                                                    chunk_rows, wgs);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

@@ -967,27 +967,45 @@ static_assert(v3_smem<false>() <= 232448 && v3_smem<true>() <= 232448,
 // bound) scaled by powers of two -- per row on the query side, one scale on the item side. K
 // chunks are still 128-byte rows (64 halves), four K = 16 MMAs each, at twice the tf32 rate and
 // half the shared-memory / L2 traffic.
-template <bool L2, bool F16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_bh,
-                const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc, int k, int pw,
-                float margin_scale, const float* __restrict__ a_norms, const float* __restrict__ b_norms,
-                int64_t a_total, int64_t b_total, float* __restrict__ part_key, int* __restrict__ part_idx,
-                int* __restrict__ row_flags, float* __restrict__ cand_key_buf, int* __restrict__ cand_idx_buf,
-                unsigned* __restrict__ gthr, const float* __restrict__ a_row_scale, float b_scale,
-                const int* __restrict__ row_map, int row_div) {
-    constexpr int STAGES = Tc3Cfg<F16>::STAGES;
+//
+// PAIR = false is the single-CTA form (cta_group::1, M = 128, every CTA streams whole 256-row
+// item tiles in 32 KB stages): one unit per CTA instead of two per CTA pair. It exists for
+// batches that are a single partial wave, where an odd number of query tiles or a phantom tile
+// keeps CTA pairs from cutting the catalog finely enough to use every SM (e.g. 49 tiles x 3
+// chunks = 147 units fill 147 of 148 SMs; 25 pairs can only be cut 2 ways = 50 of 74 pairs).
+template <bool F16, bool PAIR>
+struct Tc3Lay {
+    static constexpr int B_STAGE_BYTES = PAIR ? BH_BYTES : B_BYTES;
+    static constexpr int STAGES = PAIR ? Tc3Cfg<F16>::STAGES : Tc3Cfg<F16>::STAGES / 2;
+    static constexpr size_t SMEM = (size_t)Tc3Cfg<F16>::A_TILE_BYTES + (size_t)STAGES * B_STAGE_BYTES + sizeof(Tc3Shared<STAGES>);
+};
+static_assert(Tc3Lay<true, false>::SMEM <= 232448, "single-CTA filter kernel exceeds the shared memory per CTA");
+
+template <bool L2, bool F16, bool PAIR>
+__device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtensorMap& map_bh,
+                                         const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc,
+                                         int k, int pw, float margin_scale, const float* __restrict__ a_norms,
+                                         const float* __restrict__ b_norms, int64_t a_total, int64_t b_total,
+                                         float* __restrict__ part_key, int* __restrict__ part_idx,
+                                         int* __restrict__ row_flags, float* __restrict__ cand_key_buf,
+                                         int* __restrict__ cand_idx_buf, unsigned* __restrict__ gthr,
+                                         const float* __restrict__ a_row_scale, float b_scale,
+                                         const int* __restrict__ row_map, int row_div) {
+    constexpr int STAGES = Tc3Lay<F16, PAIR>::STAGES;
+    constexpr int BSB = Tc3Lay<F16, PAIR>::B_STAGE_BYTES;
     constexpr int KE = F16 ? 2 * KC : KC;  // elements per 128-byte K chunk
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;  // 128-byte swizzled tiles need 1024-byte alignment
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* smem_b = smem + Tc3Cfg<F16>::A_TILE_BYTES;
-    Tc3Shared<STAGES>* sh = reinterpret_cast<Tc3Shared<STAGES>*>(smem_b + (size_t)STAGES * BH_BYTES);
+    Tc3Shared<STAGES>* sh = reinterpret_cast<Tc3Shared<STAGES>*>(smem_b + (size_t)STAGES * BSB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_pairs = (*n_units_p + 1) >> 1;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    // work items: unit pairs for CTA pairs, units for single CTAs
+    const int wid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_items = PAIR ? (*n_units_p + 1) >> 1 : *n_units_p;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -996,7 +1014,7 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
         for (int a = 0; a < 2; a++) {
             ptx::mbar_init(&sh->tfull[a], 1);
-            ptx::mbar_init(&sh->tempty[a], 16);
+            ptx::mbar_init(&sh->tempty[a], PAIR ? 16 : 8);
         }
         ptx::mbar_init(&sh->afull, 1);
         ptx::mbar_init(&sh->aempty, 1);
@@ -1005,42 +1023,62 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         ptx::prefetch_tensormap(&map_bh);
     }
     if (warp == 1) {
-        ptx::tmem_alloc_cg2(&sh->tmem_base, TMEM_COLS);
-        ptx::tmem_relinquish_cg2();
+        if (PAIR) {
+            ptx::tmem_alloc_cg2(&sh->tmem_base, TMEM_COLS);
+            ptx::tmem_relinquish_cg2();
+        } else {
+            ptx::tmem_alloc(&sh->tmem_base, TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tcgen05_fence_before();
-    __syncwarp();
-    ptx::cluster_sync_all();
+    if (PAIR) {
+        __syncwarp();
+        ptx::cluster_sync_all();
+    } else {
+        __syncthreads();
+    }
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
     if (warp < EPI_WARP0) ptx::setmaxnreg_dec<40>();  // the CTA owns 12 warps x 168 registers; 4 x 40 + 8 x 232 = 12 x 168 exactly (a larger request never succeeds)
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        const uint32_t full0_base = ptx::mapa_u32(&sh->full[0], 0);
-        const uint32_t afull0 = ptx::mapa_u32(&sh->afull, 0);
+        // ------------------------------------------------------------------ TMA producer (every CTA)
+        const uint32_t full0_base = PAIR ? ptx::mapa_u32(&sh->full[0], 0) : 0u;
+        const uint32_t afull0 = PAIR ? ptx::mapa_u32(&sh->afull, 0) : 0u;
         int stage = 0;
         uint32_t phase = 0, a_phase = 0;
-        for (int p = cluster_id; p < n_pairs; p += n_clusters) {
-            const Unit un = units[2 * p + rank];
-            const int ntiles = (un.b_rows + BN - 1) / BN;
+        for (int p = wid; p < n_items; p += nworkers) {
+            const Unit un = units[PAIR ? 2 * p + (int)rank : p];
+            const int ntiles = (PAIR || un.a_rows > 0) ? (un.b_rows + BN - 1) / BN : 0;
             // the unit's query tile, once
             ptx::mbar_wait<64>(&sh->aempty, a_phase ^ 1);
             if (ptx::elect_one()) {
-                if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
-                for (int kc = 0; kc < nkc; kc++)
-                    ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KE, un.a_row0);
+                if (PAIR) {
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
+                    for (int kc = 0; kc < nkc; kc++)
+                        ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KE, un.a_row0);
+                } else {
+                    ptx::mbar_arrive_expect_tx(&sh->afull, nkc * A_BYTES);
+                    for (int kc = 0; kc < nkc; kc++)
+                        ptx::tma_load_2d(smem + (size_t)kc * A_BYTES, &map_ah, &sh->afull, kc * KE, un.a_row0);
+                }
             }
             __syncwarp();
             a_phase ^= 1;
             for (int t = 0; t < ntiles; t++) {
-                const int brow = un.b_row0 + t * BN + (int)rank * (BN / 2);
+                const int brow = un.b_row0 + t * BN + (PAIR ? (int)rank * (BN / 2) : 0);
                 for (int kc = 0; kc < nkc; kc++) {
                     ptx::mbar_wait<64>(&sh->empty[stage], phase ^ 1);
-                    const uint32_t fb = full0_base + (uint32_t)stage * 8;
                     if (ptx::elect_one()) {
-                        if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * BH_BYTES);
-                        ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BH_BYTES, &map_bh, fb, kc * KE, brow);
+                        if (PAIR) {
+                            if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->full[stage], 2 * BSB);
+                            ptx::tma_load_2d_cg2(smem_b + (size_t)stage * BSB, &map_bh, full0_base + (uint32_t)stage * 8,
+                                                 kc * KE, brow);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(&sh->full[stage], BSB);
+                            ptx::tma_load_2d(smem_b + (size_t)stage * BSB, &map_bh, &sh->full[stage], kc * KE, brow);
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) {
@@ -1051,9 +1089,10 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
         if (rank == 0) {
-            constexpr uint32_t idesc = F16 ? ptx::umma_idesc_f16(2 * BM, BN) : ptx::umma_idesc_tf32(2 * BM, BN);
+            constexpr int MM = PAIR ? 2 * BM : BM;
+            constexpr uint32_t idesc = F16 ? ptx::umma_idesc_f16(MM, BN) : ptx::umma_idesc_tf32(MM, BN);
             const uint32_t la0 = ptx::umma_desc_lo(ptx::smem_u32(smem));
             const uint32_t lb0 = ptx::umma_desc_lo(ptx::smem_u32(smem_b));
             int stage = 0;
@@ -1061,9 +1100,9 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             int acc = 0;
             uint32_t acc_phase = 0;
             uint32_t mma_gt = 0;  // running tile index (trace builds)
-            for (int p = cluster_id; p < n_pairs; p += n_clusters) {
-                const Unit un = units[2 * p];
-                const int ntiles = (un.b_rows + BN - 1) / BN;
+            for (int p = wid; p < n_items; p += nworkers) {
+                const Unit un = units[PAIR ? 2 * p : p];
+                const int ntiles = (PAIR || un.a_rows > 0) ? (un.b_rows + BN - 1) / BN : 0;
                 ptx::mbar_wait(&sh->afull, a_phase);
                 ptx::tcgen05_fence_after();
                 a_phase ^= 1;
@@ -1076,18 +1115,28 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                         ptx::mbar_wait(&sh->full[stage], phase);
                         ptx::tcgen05_fence_after();
                         const uint32_t l_a = la0 + (uint32_t)(kc * A_BYTES) / 16;
-                        const uint32_t l_b = lb0 + (uint32_t)(stage * BH_BYTES) / 16;
+                        const uint32_t l_b = lb0 + (uint32_t)(stage * BSB) / 16;
                         if (ptx::elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {  // 32 bytes of K per MMA: 8 tf32 / 16 fp16
-                                if (F16)
-                                    ptx::umma_f16_cg2(d_tmem, ptx::umma_desc_join(l_a + 2 * ks),
-                                                      ptx::umma_desc_join(l_b + 2 * ks), idesc, (kc | ks) != 0);
-                                else
-                                    ptx::umma_tf32_cg2(d_tmem, ptx::umma_desc_join(l_a + 2 * ks),
-                                                       ptx::umma_desc_join(l_b + 2 * ks), idesc, (kc | ks) != 0);
+                                const uint64_t da = ptx::umma_desc_join(l_a + 2 * ks), db = ptx::umma_desc_join(l_b + 2 * ks);
+                                const uint32_t accum = (kc | ks) != 0;
+                                if (PAIR) {
+                                    if (F16)
+                                        ptx::umma_f16_cg2(d_tmem, da, db, idesc, accum);
+                                    else
+                                        ptx::umma_tf32_cg2(d_tmem, da, db, idesc, accum);
+                                } else {
+                                    if (F16)
+                                        ptx::umma_f16(d_tmem, da, db, idesc, accum);
+                                    else
+                                        ptx::umma_tf32(d_tmem, da, db, idesc, accum);
+                                }
                             }
-                            ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);
+                            if (PAIR)
+                                ptx::umma_commit_cg2_mc(&sh->empty[stage], 3);
+                            else
+                                ptx::umma_commit(&sh->empty[stage]);
                         }
                         __syncwarp();
                         if (++stage == STAGES) {
@@ -1095,32 +1144,71 @@ topk_tc3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                             phase ^= 1;
                         }
                     }
-                    if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);
+                    if (ptx::elect_one()) {
+                        if (PAIR)
+                            ptx::umma_commit_cg2_mc(&sh->tfull[acc], 3);
+                        else
+                            ptx::umma_commit(&sh->tfull[acc]);
+                    }
                     __syncwarp();
                     NRB_TR(0, mma_gt, 1);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
                 // query tile may be replaced once these MMAs retire
-                if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&sh->aempty, 3);
+                if (ptx::elect_one()) {
+                    if (PAIR)
+                        ptx::umma_commit_cg2_mc(&sh->aempty, 3);
+                    else
+                        ptx::umma_commit(&sh->aempty);
+                }
                 __syncwarp();
             }
         }
     } else if (warp >= EPI_WARP0) {
-        // ------------------------------------------------------------------ filter epilogue (both CTAs)
+        // ------------------------------------------------------------------ filter epilogue (every CTA)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
                    row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale};
-        epilogue_run<L2, true, true>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
+        epilogue_run<L2, PAIR, true>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
     ptx::tcgen05_fence_before();
-    __syncwarp();
-    ptx::cluster_sync_all();
+    if (PAIR) {
+        __syncwarp();
+        ptx::cluster_sync_all();
+    } else {
+        __syncthreads();
+    }
     if (warp == 1) {
         ptx::tcgen05_fence_after();
-        ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+        if (PAIR)
+            ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+        else
+            ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+#define NRB_TC3_PARAMS                                                                                              \
+    const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_bh,                         \
+        const Unit *__restrict__ units, const int *__restrict__ n_units_p, int nkc, int k, int pw, float margin_scale, \
+        const float *__restrict__ a_norms, const float *__restrict__ b_norms, int64_t a_total, int64_t b_total,    \
+        float *__restrict__ part_key, int *__restrict__ part_idx, int *__restrict__ row_flags,                     \
+        float *__restrict__ cand_key_buf, int *__restrict__ cand_idx_buf, unsigned *__restrict__ gthr,             \
+        const float *__restrict__ a_row_scale, float b_scale, const int *__restrict__ row_map, int row_div
+#define NRB_TC3_ARGS                                                                                                  \
+    map_ah, map_bh, units, n_units_p, nkc, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx, \
+        row_flags, cand_key_buf, cand_idx_buf, gthr, a_row_scale, b_scale, row_map, row_div
+
+template <bool L2, bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) topk_tc3_kernel(NRB_TC3_PARAMS) {
+    tc3_body<L2, F16, true>(NRB_TC3_ARGS);
+}
+
+// single-CTA form (fp16 planes only)
+template <bool L2>
+__global__ void __launch_bounds__(NUM_THREADS, 1) topk_tc3s_kernel(NRB_TC3_PARAMS) {
+    tc3_body<L2, true, false>(NRB_TC3_ARGS);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -1282,7 +1370,8 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
-                        cudaStream_t st) {
+                        int single, cudaStream_t st) {
+    NRB_REQUIRE(!single || f16, "tc1: the single-CTA form exists for the fp16 planes only");
     // what the KERNEL reads (the raw planes are the refine stage's business: *_eligible)
     if (f16)
         NRB_REQUIRE(a->h16 && a->h16_row_scale && b->h16 && b->h16_scale > 0.f, "tc16: scaled fp16 planes required");
@@ -1291,7 +1380,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
     NRB_REQUIRE(a->norms && b->norms && a->kp == b->kp && a->kp <= V3_MAX_NKC * KC && tc1_k_ok(k) && row_div >= 1,
                 "tc1: norms on both sides, kp <= 256 and k <= %d required", TC1_MAX_PW - TC1_MIN_EXTRA);
     NRB_REQUIRE(a->kp % KC == 0 && pw >= k && pw <= CAND_CAP - HALF_N, "tc1: bad kp / pw");
-    NRB_REQUIRE(grid >= 2 && grid % 2 == 0, "tc1: grid must be a positive even number");
+    NRB_REQUIRE(grid >= 1 && (single || grid % 2 == 0), "tc1: grid must be positive (and even for CTA pairs)");
     if (scratch_bytes < tc_scratch_bytes(grid)) {
         set_error("tc1: scratch too small");
         return NRB_ERR_WORKSPACE;
@@ -1300,7 +1389,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
     int rc;
     if (f16) {
         if ((rc = make_plane_map_h16(&mah, a->h16, a->n, a->kp, BM))) return rc;
-        if ((rc = make_plane_map_h16(&mbh, b->h16, b->n, b->kp, BN / 2))) return rc;
+        if ((rc = make_plane_map_h16(&mbh, b->h16, b->n, b->kp, single ? BN : BN / 2))) return rc;
     } else {
         if ((rc = make_plane_map(&mah, a->hi, a->n, a->kp, BM))) return rc;
         if ((rc = make_plane_map(&mbh, b->hi, b->n, b->kp, BN / 2))) return rc;
@@ -1319,7 +1408,20 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                                                                       part_key, part_idx, row_flags, ck, ci, gthr,  \
                                                                       ars, bsc, row_map, row_div);                  \
     } while (0)
-    if (metric == NRB_METRIC_L2) {
+    if (single) {
+        constexpr size_t SM1 = Tc3Lay<true, false>::SMEM;
+        if (metric == NRB_METRIC_L2) {
+            NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM1));
+            topk_tc3s_kernel<true><<<grid, NUM_THREADS, SM1, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
+                                                                   a->norms, b->norms, a->n, b->n, part_key, part_idx,
+                                                                   row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
+        } else {
+            NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM1));
+            topk_tc3s_kernel<false><<<grid, NUM_THREADS, SM1, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
+                                                                    a->norms, b->norms, a->n, b->n, part_key, part_idx,
+                                                                    row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
+        }
+    } else if (metric == NRB_METRIC_L2) {
         if (f16)
             NRB_TC3_LAUNCH(true, true);
         else

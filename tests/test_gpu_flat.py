@@ -332,3 +332,19 @@ def test_growing_norms_repack_fp16_plane(nf, oracle):
         Do, Io = oracle.knn_fast(xq, xb, 20, metric)
         rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
         assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_single_cta_filter_kernel(nf, oracle, metric, monkeypatch):
+    """The single-CTA (cta_group::1, M = 128) form of the fp16 filter kernel, which the planner picks
+    for single partial waves where CTA pairs cannot cut the catalog finely enough: forced here on
+    shapes with odd tile counts, ragged tiles and several item chunks."""
+    monkeypatch.setenv("NRB_FORCE_SINGLE_CTA", "1")
+    rng = np.random.default_rng(90 + metric)
+    for nq, nb, d, k in ((1, 3000, 250, 50), (129, 70000, 250, 50), (385, 30011, 96, 20), (6250, 20000, 64, 10)):
+        xb = rng.standard_normal((nb, d), dtype=np.float32)
+        xq = rng.standard_normal((nq, d), dtype=np.float32)
+        D, I = _search(nf, xb, xq, k, metric, "tc16")
+        Do, Io = oracle.knn_fast(xq, xb, k, metric)
+        rep = compare_topk(D, I, Do, Io, metric, scale=_l2_scale(xq, xb) if metric == 1 else None)
+        assert rep["ok"], (nq, nb, d, k, rep)
