@@ -110,3 +110,28 @@ def test_shim_exposes_reference_surface():
     finally:
         sys.path.pop(0)
         sys.modules.pop("faiss", None)
+
+
+def test_matrix_struct_layout_matches_header(tmp_path):
+    """struct nrb_matrix as bound by ctypes has the size and field offsets gcc gives the header."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields = [f[0] for f in _lib.Matrix._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(nrb_matrix, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nrb200.h"\n'
+                   'int main(void){printf("%zu\\n", sizeof(nrb_matrix));' + body + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert out[0] == C.sizeof(_lib.Matrix)
+    assert out[1:] == [getattr(_lib.Matrix, f).offset for f in fields]
+
+
+def test_h16_scale_is_a_power_of_two_with_headroom():
+    import math
+    import newsrecommend_b200.faiss as nf
+    for mx in (1e-30, 3e-5, 0.75, 1.0, 15.8, 16.0, 1234.5, 6.0e4, 1e20):
+        s = nf._h16_scale_for(mx)
+        assert math.log2(s) == round(math.log2(s))
+        assert 2.0 ** 14 <= mx * s < 2.0 ** 15 or mx < 2.0 ** -60 or mx > 2.0 ** 60
+    assert nf._h16_scale_for(0.0) == 1.0 and nf._h16_scale_for(float("inf")) == 1.0
