@@ -1,33 +1,38 @@
-// K2: fused distance + selection on the 5th-generation tensor cores (NRB_PATH_TC).
+// K2: fused distance + selection on the 5th-generation tensor cores (NRB_PATH_TC, NRB_PATH_TC1,
+// NRB_PATH_TC16).
 //
 // Stands in for faiss's exhaustive_inner_product_blas / exhaustive_L2sqr_blas (sgemm blocks +
 // HeapBlockResultHandler) behind IndexFlat::search, i.e. Retrieval.py:21,32 and the assignment
-// search inside Clustering::train (Retrieval.py:18).
+// search inside Clustering::train (Retrieval.py:18), and for IVFFlatScanner over list units.
 //
-// Persistent CTAs walk a list of Units (128 query rows x a run of item rows). Per 128 x 256
-// score tile:
-//   warp 0  (1 lane)  TMA producer: hi/lo planes of the query tile and the item tile, K chunks
-//                     of 32 fp32 (128-byte swizzled rows), mbarrier ring
-//   warp 1  (1 lane)  MMA issuer: per K step three tcgen05.mma.kind::tf32 into ONE fp32 TMEM
-//                     accumulator -- lo*hi, hi*lo, hi*hi (3xTF32, small terms first)
-//   warps 2-5, 6-9    two epilogue warpgroups; warpgroup g takes columns [128g, 128g+128) of EVERY
-//                     tile (so the epilogue runs back to back while the other accumulator's
-//                     MMAs execute): tcgen05.ld 128 x 128 scores (one query row per thread),
-//                     turn scores into keys, append everything above the row's running
-//                     threshold to the row's candidate buffer; a warp-cooperative bitonic
-//                     prune brings a full buffer back to the best k and raises the threshold.
-//                     Each warpgroup keeps its own per-row state and writes its own partial
-//                     rows (merged later by the k-way merge).
-// TMEM holds two accumulators (2 x 256 columns) so the epilogues overlap the MMAs of the next
-// tiles. The score matrix never exists in HBM.
+// Persistent CTAs (384 threads = three hardware warpgroups) walk a list of Units (128 query rows
+// x a run of item rows). Per 128 x 256 score tile:
+//   warp 0            TMA producer: operand tiles in K chunks of 128 bytes (128-byte swizzle),
+//                     mbarrier ring
+//   warp 1            MMA issuer: tcgen05.mma into one of two fp32 TMEM accumulators (2 x 256
+//                     columns), so the MMAs of tile t+1 overlap the selection of tile t
+//   warps 2-3         idle (they complete the control warpgroup, which gives its registers to
+//                     the selection warpgroups with setmaxnreg)
+//   warps 4-7, 8-11   two selection warpgroups; warpgroup g owns columns [128g, 128g+128) of EVERY
+//                     tile: tcgen05.ld 32 rows x 128 scores into registers (one query row per
+//                     thread), hand the accumulator back, then skip / append: group maxima decide
+//                     per 32-column chunk whether anything beats the row's running threshold, and
+//                     only then are keys appended to the row's candidate buffer. Thresholds are
+//                     tightened by scheduled prunes (bisection + compaction on the union of the
+//                     two warpgroups' buffers); an exact bitonic sort per row ends the unit.
+// The score matrix never exists in HBM.
 //
-// Two variants share the epilogue:
-//   v2 (default)  CTA pairs, tcgen05.mma.cta_group::2 with M = 256: the two CTAs of a cluster
-//                 take two adjacent units that share their item rows; each CTA stages its own
-//                 128 query rows and HALF of the 256-row item tile, so the item stream is read
-//                 from L2 once per 256 queries. 3 stages x 64 KB per CTA.
-//   v1            one CTA per unit, cta_group::1, M = 128; 2 stages x 96 KB. Kept as the
-//                 simpler cross-check (nrb_set_tc_variant(1)).
+// Kernels (shared epilogue, epilogue_run):
+//   topk_tc3_kernel<fp16|tf32>  filter: ONE pass over reduced-precision operand planes (scaled fp16,
+//                 or the tf32 hi planes), query tile resident in shared memory, CTA pairs
+//                 (cta_group::2, M = 256); keeps the best k plus everything inside a proven
+//                 error margin, exact fp32 refine follows (select_refine_kernel). Default.
+//   topk_tc3s_kernel            its single-CTA form (cta_group::1, M = 128) for single partial waves.
+//   topk_tc2_kernel             3xTF32: per K step lo*hi, hi*lo, hi*hi into one accumulator, CTA
+//                 pairs; each CTA stages its own 128 query rows and HALF of the 256-row item
+//                 tile, so the item stream is read from L2 once per 256 queries. 3 x 64 KB stages.
+//   topk_tc_kernel              3xTF32, one CTA per unit, 2 x 96 KB stages; the simpler
+//                 cross-check (nrb_set_tc_variant(1)).
 #include <cuda.h>
 
 #include <cstdlib>

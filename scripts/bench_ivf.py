@@ -10,6 +10,8 @@ from newsrecommend_b200.parity import compare_topk, recall_at_k
 from oracle import faiss_oracle as fo
 
 NLISTS = [int(a) for a in sys.argv[1:]] or [250]
+if os.environ.get("NRB_IVF_BATCH"):
+    nf.IVF_QUERY_BATCH = int(os.environ["NRB_IVF_BATCH"])  # queries per nrb_ivf_search call
 NQ = int(os.environ.get("NRB_IVF_NQ", "250000"))
 L2 = os.environ.get("NRB_IVF_METRIC", "ip") == "l2"
 MET = 1 if L2 else 0
