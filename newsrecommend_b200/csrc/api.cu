@@ -299,7 +299,12 @@ __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __
     }
 }
 
-constexpr int IVF_CHUNK = 8192;  // item rows per unit inside one list (long runs amortise the per-unit prunes)
+// item rows per unit inside one list: long runs amortise the per-unit prunes and sorts (sweep on config 2:
+// 4,096 -> 40.4 ms, 8,192 -> 36.2, 16,384 -> 35.4, 32,768 -> 33.8); NRB_IVF_CHUNK overrides
+static int ivf_chunk() {
+    static const int v = getenv("NRB_IVF_CHUNK") ? atoi(getenv("NRB_IVF_CHUNK")) : 32768;
+    return v >= 256 ? (v + 255) / 256 * 256 : 32768;
+}
 
 struct IvfPlan {
     int64_t npairs;
@@ -309,7 +314,7 @@ struct IvfPlan {
 static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int path) {
     IvfPlan p;
     p.npairs = nq * nprobe;
-    p.maxsplit = (max_list_len + IVF_CHUNK - 1) / IVF_CHUNK;
+    p.maxsplit = (max_list_len + ivf_chunk() - 1) / ivf_chunk();
     if (p.maxsplit < 1) p.maxsplit = 1;
     int64_t mu = (p.npairs / UNIT_ROWS + 2 * (int64_t)nlist) * p.maxsplit;
     p.max_units = (int)mu;
@@ -618,7 +623,7 @@ static int ivf_search_impl(const nrb_matrix* q, const nrb_matrix* lists, const i
     if ((rc = launch_counting_sort_i64(coarse, p.npairs, nlist, w.p_off, w.order, w.pos_of, w.cs, w.cs_bytes, st))) return rc;
     // 2. units + src table, all on the device
     const size_t sh = (size_t)(nlist + 1) * sizeof(int);
-    ivf_plan_kernel<<<1, 512, sh, st>>>(w.p_off, offsets, nlist, IVF_CHUNK, w.ubase, w.nsl, w.n_units, w.units, p.max_units);
+    ivf_plan_kernel<<<1, 512, sh, st>>>(w.p_off, offsets, nlist, ivf_chunk(), w.ubase, w.nsl, w.n_units, w.units, p.max_units);
     NRB_LAUNCH_CHECK();
     {
         int64_t blocks = (p.npairs + 255) / 256;
