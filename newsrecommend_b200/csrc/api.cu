@@ -302,7 +302,8 @@ __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __
 // item rows per unit inside one list: long runs amortise the per-unit prunes and sorts (sweep on config 2:
 // 4,096 -> 40.4 ms, 8,192 -> 36.2, 16,384 -> 35.4, 32,768 -> 33.8); NRB_IVF_CHUNK overrides
 static int ivf_chunk() {
-    static const int v = getenv("NRB_IVF_CHUNK") ? atoi(getenv("NRB_IVF_CHUNK")) : 32768;
+    const char* e = getenv("NRB_IVF_CHUNK");  // read per call: tests force small runs to cover split lists
+    const int v = e ? atoi(e) : 32768;
     return v >= 256 ? (v + 255) / 256 * 256 : 32768;
 }
 

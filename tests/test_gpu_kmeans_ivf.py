@@ -213,3 +213,23 @@ def test_ivf_filter_fallback_on_duplicates(nf, oracle):
         assert len(set(I[q].tolist())) == 10 and (I[q] // 150 == q).all()
     Do, Io = oracle.knn_fast(xq, xb, 10, 0)
     assert np.allclose(D, Do, rtol=1e-4)
+
+
+@pytest.mark.parametrize("path", [4, 2])
+def test_ivf_lists_split_into_several_units(nf, oracle, path, monkeypatch):
+    """Lists longer than the item run of a unit are scanned as several units whose partial results
+    are merged per query: forced here with 512-row runs (default 32,768); nprobe = nlist = exact."""
+    monkeypatch.setenv("NRB_IVF_CHUNK", "512")
+    from newsrecommend_b200 import synth
+    xb, topics = synth.g_skew(30000, 64, 71, n_topics=40, return_topics=True)
+    xq = synth.user_profiles(xb, topics, 300, 72)
+    ivf = nf.IndexIVFFlat(nf.IndexFlatIP(64), 64, 8, nf.METRIC_INNER_PRODUCT)
+    ivf.path = path
+    ivf.train(xb)
+    ivf.add(xb)
+    assert ivf.list_sizes().max() > 2048  # at least five runs in the longest list
+    ivf.nprobe = 8
+    D, I = ivf.search(xq, 20)
+    Do, Io = oracle.knn_fast(xq, xb, 20, 0)
+    rep = compare_topk(D, I, Do, Io, 0)
+    assert rep["ok"], rep
