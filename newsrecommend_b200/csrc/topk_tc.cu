@@ -70,6 +70,8 @@ constexpr int V2_STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;  // 64 KB
 // the rows between them, and read the new state back.
 struct XchgShared {
     int cnt[EPI_WGS][BM];    // in: the row's buffered entries per warpgroup; out: entries kept
+    int fresh[EPI_WGS][BM];  // in: entries appended since the row's last prune
+    int done[BM];            // out: 1 if the row was pruned (0: too few new entries, left as it is)
     float thr[EPI_WGS][BM];  // in: each warpgroup's append threshold for the row
     float margin[BM];        // in: the row's error margin (filter kernels; else 0)
     float nthr[BM];          // out: new append threshold (both warpgroups)
@@ -330,8 +332,12 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
 // with more than 128 entries (possible only after heavy ties) are first brought down by the
 // single-buffer prune.
 constexpr int UT_SLACK = 3;
+// min_new > 0 (units that share running bounds with other units of the same query: IVF lists):
+// a row pair is pruned only once min_new new candidates have arrived in one of its rows -- rows
+// whose threshold was already hot when the unit started are left alone and the scheduled prune
+// costs them nothing but the barrier (IVF scan -5 %; the flat search prunes every row anyway).
 __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, int* ci_cta, int quad, int half,
-                                                int k, int keep_max) {
+                                                int k, int keep_max, int min_new) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll 1
@@ -340,6 +346,13 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
         float *kA[2], *kB[2];
         int *iA[2], *iB[2];
         float floor_t[2], mg[2];
+        if (min_new > 0) {
+            const int r0 = quad * 32 + half * 16 + 2 * it, r1 = r0 + 1;
+            if (xs->fresh[0][r0] + xs->fresh[1][r0] < min_new && xs->fresh[0][r1] + xs->fresh[1][r1] < min_new) {
+                if (lane < 2) xs->done[r0 + lane] = 0;
+                continue;  // warp-uniform
+            }
+        }
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             row[b] = quad * 32 + half * 16 + 2 * it + b;
@@ -471,6 +484,7 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                 xs->cnt[1][row[b]] = baseB;
                 xs->nthr[row[b]] = thr;
                 xs->lb[row[b]] = lo[b];
+                xs->done[row[b]] = 1;
             }
         }
         __syncwarp();
@@ -628,23 +642,27 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             const uint32_t tp = (uint32_t)t + 1u;
             if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles) {
                 xs->cnt[wg][row] = st.cnt;
+                xs->fresh[wg][row] = st.cnt - st.base;
                 xs->thr[wg][row] = st.thr;
                 if (wg == 0) xs->margin[row] = st.margin;
                 NRB_TRP(warp - EPI_WARP0 + 1, 0);
                 ptx::named_bar_sync(3 + quad, 64);
                 NRB_TRP(warp - EPI_WARP0 + 1, 1);
                 union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
-                                   A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw);
+                                   A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw,
+                                   A.row_map ? max(4, A.k >> 2) : 0);
                 NRB_TRP(warp - EPI_WARP0 + 1, 2);
                 ptx::named_bar_sync(3 + quad, 64);
                 NRB_TRP(warp - EPI_WARP0 + 1, 3);
                 NRB_TRP_NEXT(warp - EPI_WARP0 + 1);
-                st.cnt = xs->cnt[wg][row];
-                st.base = st.cnt;
-                st.thr = xs->nthr[row];
-                st.cthr = L2 ? st.thr : st.thr * st.sc;
-                const uint32_t lbu = xs->lb[row];
-                if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
+                if (xs->done[row]) {
+                    st.cnt = xs->cnt[wg][row];
+                    st.base = st.cnt;
+                    st.thr = xs->nthr[row];
+                    st.cthr = L2 ? st.thr : st.thr * st.sc;
+                    const uint32_t lbu = xs->lb[row];
+                    if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
+                }
             }
         }
         epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
