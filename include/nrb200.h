@@ -124,6 +124,13 @@ int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, in
  * (candidate slots exhausted inside the error margin, or an estimate outside its bound). */
 int64_t nrb_fallback_query_count(void);
 
+/* The work plan nrb_search_flat would use (host logic only, no device needed; 148 SMs are assumed
+ * when there is no device): out10 = { query tiles, tile pairs, full pairs (one pass over the whole
+ * catalog each), tail pairs, item chunks per tail pair (or per tile), item rows per chunk, units,
+ * partial-result slots per query, CTAs launched, 1 if the single-CTA kernel form is used }.
+ * path must be a concrete NRB_PATH_* (not AUTO). */
+int nrb_plan_flat_describe(int64_t nq, int64_t nb, int32_t k, int32_t path, int32_t* out10);
+
 /* ---- K1b: k-means centroid update (Clustering.cpp compute_centroids) ---------------------- */
 /* Replaces the update step of clustering.train (Retrieval.py:18). x_raw is the packed raw
  * plane [n, kp]; assign i64[n] in [0, k). Writes centroids f32[k, d] (row stride d) as the

@@ -578,6 +578,16 @@ extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t
 
 extern "C" int64_t nrb_fallback_query_count(void) { return (int64_t)g_fallback_queries.load(); }
 
+extern "C" int nrb_plan_flat_describe(int64_t nq, int64_t nb, int32_t k, int32_t path, int32_t* out10) {
+    NRB_REQUIRE(out10 && nq >= 1 && nb >= 0 && k >= 1 && k <= NRB_MAX_K, "plan_flat_describe: bad arguments");
+    NRB_REQUIRE(path == NRB_PATH_SIMT || path == NRB_PATH_TC || path == NRB_PATH_TC1 || path == NRB_PATH_TC16,
+                "plan_flat_describe: path must be a concrete path, not %d", path);
+    const FlatPlan p = plan_flat(nq, nb, k, path);
+    const int v[10] = {p.nqt, p.npairs, p.full_pairs, p.tail_pairs, p.tsplit, p.chunk_rows, p.n_units, p.S, p.grid, p.single};
+    for (int i = 0; i < 10; i++) out10[i] = v[i];
+    return NRB_OK;
+}
+
 extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k, int32_t kp,
                                            int32_t nlist, int32_t max_list_len) {
     if (nq <= 0 || nprobe <= 0 || k <= 0) return 256;

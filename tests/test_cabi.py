@@ -135,3 +135,45 @@ def test_h16_scale_is_a_power_of_two_with_headroom():
         assert math.log2(s) == round(math.log2(s))
         assert 2.0 ** 14 <= mx * s < 2.0 ** 15 or mx < 2.0 ** -60 or mx > 2.0 ** 60
     assert nf._h16_scale_for(0.0) == 1.0 and nf._h16_scale_for(float("inf")) == 1.0
+
+
+def _plan(nq, nb, k, path):
+    out = (C.c_int32 * 10)()
+    assert _lib.lib.nrb_plan_flat_describe(nq, nb, k, path, out) == 0, _lib.last_error()
+    names = ("nqt", "npairs", "full_pairs", "tail_pairs", "tsplit", "chunk_rows", "n_units", "S", "grid", "single")
+    return dict(zip(names, list(out)))
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.get_device_properties(0).multi_processor_count != 148,
+                    reason="expectations are written for 148 SMs")
+def test_flat_planner_invariants_and_known_plans():
+    """Host logic of the flat search plan (csrc/api.cu plan_flat), checked without a device."""
+    TC, TC16, SIMT = _lib.PATH_TC, _lib.PATH_TC16, _lib.PATH_SIMT
+    # config 1: 50,000 queries = 391 tiles = 196 pairs = 2 full waves of 74 + 48 tail pairs cut 2..4 ways
+    p = _plan(50000, 364047, 50, TC16)
+    assert (p["nqt"], p["npairs"], p["full_pairs"], p["tail_pairs"], p["single"]) == (391, 196, 148, 48, 0)
+    assert 2 <= p["tsplit"] <= 4 and p["grid"] == 148 and p["n_units"] == 2 * (148 + 48 * p["tsplit"])
+    # 6,250 queries per GPU (N = 8): 49 tiles; CTA pairs stop at 2 chunks, single CTAs take 3 (147 of 148 SMs)
+    p = _plan(6250, 364047, 50, TC16)
+    assert (p["nqt"], p["single"], p["tsplit"], p["n_units"], p["grid"]) == (49, 1, 3, 147, 147)
+    assert _plan(6250, 364047, 50, TC)["single"] == 0  # the 3xTF32 kernels have no single-CTA form
+    # invariants over a sweep
+    for path in (TC, TC16, SIMT):
+        for nq in (1, 127, 128, 129, 1000, 6250, 18944, 18945, 50000, 250000):
+            for nb in (1, 255, 256, 5000, 364047):
+                p = _plan(nq, nb, 10, path)
+                assert p["nqt"] == (nq + 127) // 128 and p["npairs"] == (p["nqt"] + 1) // 2
+                assert p["chunk_rows"] % 256 == 0 and p["chunk_rows"] * p["tsplit"] >= nb
+                assert p["chunk_rows"] * (p["tsplit"] - 1) < max(nb, 1)  # no empty chunk
+                assert p["S"] == p["tsplit"] * (1 if path == SIMT else 2)
+                if p["single"]:
+                    assert path == TC16 and p["full_pairs"] == 0 and p["n_units"] == p["nqt"] * p["tsplit"]
+                    assert 1 <= p["grid"] <= 148
+                else:
+                    assert p["full_pairs"] + p["tail_pairs"] == p["npairs"]
+                    assert p["n_units"] == 2 * (p["full_pairs"] + p["tail_pairs"] * p["tsplit"])
+                    assert p["grid"] >= 1 and (path == SIMT or p["grid"] % 2 == 0)
+                if p["full_pairs"]:
+                    assert p["full_pairs"] % (148 if path == SIMT else 74) == 0
+    bad = (C.c_int32 * 10)()
+    assert _lib.lib.nrb_plan_flat_describe(10, 10, 5, _lib.PATH_AUTO, bad) == -1
