@@ -332,30 +332,38 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
 // with more than 128 entries (possible only after heavy ties) are first brought down by the
 // single-buffer prune.
 constexpr int UT_SLACK = 3;
+#ifndef NRB_UT_ROWS
+#define NRB_UT_ROWS 2
+#endif
+constexpr int UT_ROWS = NRB_UT_ROWS;  // rows of a scheduled prune in flight together (2; 4 measured: flat +0 %, IVF -17 %)
 // min_new > 0 (units that share running bounds with other units of the same query: IVF lists):
 // a row pair is pruned only once min_new new candidates have arrived in one of its rows -- rows
 // whose threshold was already hot when the unit started are left alone and the scheduled prune
 // costs them nothing but the barrier (IVF scan -5 %; the flat search prunes every row anyway).
 __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, int* ci_cta, int quad, int half,
                                                 int k, int keep_max, int min_new) {
+    constexpr int NB = UT_ROWS;  // rows in flight: their loads and reduction chains overlap
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll 1
-    for (int it = 0; it < 8; it++) {
-        int row[2], nA[2], nB[2];
-        float *kA[2], *kB[2];
-        int *iA[2], *iB[2];
-        float floor_t[2], mg[2];
+    for (int it = 0; it < 16 / NB; it++) {
+        int row[NB], nA[NB], nB[NB];
+        float *kA[NB], *kB[NB];
+        int *iA[NB], *iB[NB];
+        float floor_t[NB], mg[NB];
         if (min_new > 0) {
-            const int r0 = quad * 32 + half * 16 + 2 * it, r1 = r0 + 1;
-            if (xs->fresh[0][r0] + xs->fresh[1][r0] < min_new && xs->fresh[0][r1] + xs->fresh[1][r1] < min_new) {
-                if (lane < 2) xs->done[r0 + lane] = 0;
+            const int r0 = quad * 32 + half * 16 + NB * it;
+            bool quiet = true;
+#pragma unroll
+            for (int b = 0; b < NB; b++) quiet = quiet && (xs->fresh[0][r0 + b] + xs->fresh[1][r0 + b] < min_new);
+            if (quiet) {
+                if (lane < NB) xs->done[r0 + lane] = 0;
                 continue;  // warp-uniform
             }
         }
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
-            row[b] = quad * 32 + half * 16 + 2 * it + b;
+        for (int b = 0; b < NB; b++) {
+            row[b] = quad * 32 + half * 16 + NB * it + b;
             kA[b] = ck_cta + (int64_t)row[b] * CAND_CAP;
             iA[b] = ci_cta + (int64_t)row[b] * CAND_CAP;
             kB[b] = kA[b] + (int64_t)BM * CAND_CAP;
@@ -389,10 +397,10 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
         // All 32 loads are UNCONDITIONAL (entries beyond a buffer's count are inside its 256-entry
         // allocation and are masked afterwards): predicated loads were issued a few at a time, each
         // batch waiting for the previous one -- eight L2 round trips per row pair instead of one.
-        float rk[2][8];
-        int id[2][8];
+        float rk[NB][8];
+        int id[NB][8];
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NB; b++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int e = i * 32 + lane;
@@ -402,9 +410,9 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                 id[b][4 + i] = iB[b][e];
             }
         }
-        uint32_t u[2][8];
+        uint32_t u[NB][8];
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NB; b++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int e = i * 32 + lane;
@@ -413,10 +421,10 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
             }
         }
         __syncwarp();
-        uint32_t lo[2], hi[2];
-        bool run[2];
+        uint32_t lo[NB], hi[NB];
+        bool run[NB];
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NB; b++) {
             uint32_t mn = 0xffffffffu, mx = 0u;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -430,21 +438,25 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
             hi[b] = mx + 1u;
             run[b] = run[b] && (hi[b] - lo[b] > 1u);
         }
-        while (run[0] || run[1]) {  // warp-uniform
-            uint32_t mid[2];
-            int c[2];
+        bool any_run = false;
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NB; b++) any_run = any_run || run[b];
+        while (any_run) {  // warp-uniform
+            uint32_t mid[NB];
+            int c[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
                 mid[b] = lo[b] + ((hi[b] - lo[b]) >> 1);
                 int cc = 0;
 #pragma unroll
                 for (int i = 0; i < 8; i++) cc += (u[b][i] >= mid[b]) ? 1 : 0;
                 c[b] = cc;
             }
-            c[0] = __reduce_add_sync(0xffffffffu, c[0]);
-            c[1] = __reduce_add_sync(0xffffffffu, c[1]);
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
+            for (int b = 0; b < NB; b++) c[b] = __reduce_add_sync(0xffffffffu, c[b]);
+            any_run = false;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
                 if (run[b]) {
                     if (c[b] >= k) {
                         lo[b] = mid[b];
@@ -454,10 +466,11 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                     }
                     if (hi[b] - lo[b] <= 1u) run[b] = false;
                 }
+                any_run = any_run || run[b];
             }
         }
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NB; b++) {
             const float thr = fmaxf(from_ordered_u32(lo[b]) - mg[b], floor_t[b]);  // lo == 0 -> NEG_INF
             int baseA = 0, baseB = 0;
 #pragma unroll
