@@ -35,4 +35,19 @@ xs = clus.subsample(x)  # 6000 > 20*256 -> the iterations run on the rand_perm(1
 np.savez_compressed(os.path.join(HERE, "kmeans_small.npz"), x=x, xs=xs,
                     cin=np.stack([t[0] for t in trace]), assign=np.stack([t[1] for t in trace]),
                     cout=np.stack([t[2] for t in trace]), centroids=clus.centroids)
+# IVF-Flat: trained centroids, list sizes and nprobe = 4 results for both metrics
+xi, topics = synth.g_skew(8000, 64, 11, n_topics=40, r=8, return_topics=True)
+qi = synth.user_profiles(xi, topics, 64, 12)
+ivf_out = dict(xb=xi, xq=qi)
+for metric, qcls in ((0, fo.IndexFlatIP), (1, fo.IndexFlatL2)):
+    quant = qcls(64)
+    ivf = fo.IndexIVFFlat(quant, 64, 16, metric)
+    ivf.train(xi)
+    ivf.add(xi)
+    ivf.nprobe = 4
+    D, I = ivf.search(qi, 10)
+    ivf_out[f"cent{metric}"] = quant.xb.copy()
+    ivf_out[f"sizes{metric}"] = ivf.list_sizes()
+    ivf_out[f"D{metric}"], ivf_out[f"I{metric}"] = D, I
+np.savez_compressed(os.path.join(HERE, "ivf_small.npz"), **ivf_out)
 print("golden fixtures written")

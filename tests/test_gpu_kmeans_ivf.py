@@ -233,3 +233,23 @@ def test_ivf_lists_split_into_several_units(nf, oracle, path, monkeypatch):
     Do, Io = oracle.knn_fast(xq, xb, 20, 0)
     rep = compare_topk(D, I, Do, Io, 0)
     assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("path", [0, 4, 2, 1])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_ivf_golden_fixture(nf, metric, path):
+    """tests/golden/ivf_small.npz (written by the oracle): with the fixture's centroids in the coarse
+    quantizer the GPU index builds lists of the same sizes and returns the fixture's (D, I)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ivf_small.npz"))
+    quant = nf.IndexFlatIP(64) if metric == 0 else nf.IndexFlatL2(64)
+    quant.add(g[f"cent{metric}"])
+    ivf = nf.IndexIVFFlat(quant, 64, 16, metric)
+    ivf.path = path
+    ivf.train(g["xb"])  # the quantizer already holds 16 centroids: no retraining
+    ivf.add(g["xb"])
+    assert np.array_equal(ivf.list_sizes(), g[f"sizes{metric}"])
+    ivf.nprobe = 4
+    D, I = ivf.search(g["xq"], 10)
+    rep = compare_topk(D, I, g[f"D{metric}"], g[f"I{metric}"], metric)
+    assert rep["id_mismatch_queries"] == 0 and rep["score_violations"] == 0, rep

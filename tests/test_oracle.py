@@ -175,6 +175,23 @@ def test_golden_flat(oracle):
         assert np.array_equal(g[f"I{metric}"], g[f"It{metric}"])
 
 
+def test_golden_ivf(oracle):
+    """IVF-Flat fixture: the oracle retrains to the same centroids (deterministic k-means: mt19937
+    subsample / init, sequential fp32 sums), builds the same lists and returns the same (D, I)."""
+    g = np.load(os.path.join(GOLDEN, "ivf_small.npz"))
+    for metric, qcls in ((0, oracle.IndexFlatIP), (1, oracle.IndexFlatL2)):
+        quant = qcls(64)
+        ivf = oracle.IndexIVFFlat(quant, 64, 16, metric)
+        ivf.train(g["xb"])
+        assert np.allclose(quant.xb, g[f"cent{metric}"], rtol=1e-6, atol=1e-6)
+        ivf.add(g["xb"])
+        assert np.array_equal(ivf.list_sizes(), g[f"sizes{metric}"])
+        ivf.nprobe = 4
+        D, I = ivf.search(g["xq"], 10)
+        assert np.array_equal(I, g[f"I{metric}"])
+        assert np.allclose(D, g[f"D{metric}"], rtol=1e-6, atol=1e-6)
+
+
 def test_comparator_rejects_wrong_ids():
     D = np.array([[5.0, 4.0, 3.0]])
     I = np.array([[1, 2, 3]])
