@@ -167,7 +167,8 @@ struct FlatWs {
     int* src;
     float* part_key;
     int* part_idx;
-    int *flags, *flag_list, *flag_count;  // NRB_PATH_TC1 only
+    int* part_cnt;                        // filter paths: entries per (unsorted) partial row
+    int *flags, *flag_list, *flag_count;  // filter paths only
     unsigned* gthr;                       // per-query shared bounds (tcgen05 paths)
     void* scratch;
     size_t scratch_bytes;
@@ -184,9 +185,10 @@ static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int pat
     w.src = c.take<int>((size_t)nq * p.S);
     w.part_key = c.take<float>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
     w.part_idx = c.take<int>((size_t)p.n_units * p.wgs * UNIT_ROWS * pw);
-    w.flags = w.flag_list = w.flag_count = nullptr;
+    w.flags = w.flag_list = w.flag_count = w.part_cnt = nullptr;
     w.gthr = path == NRB_PATH_SIMT ? nullptr : c.take<unsigned>(nq);
     if (filt) {
+        w.part_cnt = c.take<int>((size_t)p.n_units * p.wgs * UNIT_ROWS);
         w.flags = c.take<int>(nq);
         w.flag_list = c.take<int>(nq);
         w.flag_count = c.take<int>(1);
@@ -225,13 +227,26 @@ static int resolve_path(int path) { return path == NRB_PATH_SIMT ? NRB_PATH_SIMT
 static std::atomic<long long> g_fallback_queries{0};
 
 // ------------------------------------------------------------------------------ IVF grouping
+// The scan runs in up to two PHASES, each with its own grouping of (query, list) pairs by list:
+//   phase A: every query's closest list (coarse rank 0), cold start -- it ends with the k-th best
+//            of that list in the query's shared running bound gthr[query];
+//   phase B: the other nprobe - 1 lists, which start from that bound: nearly every 32-column
+//            chunk is skipped by the first compare, rows end with a handful of candidates and
+//            need no prune at all.
+// (One pass over all nprobe lists in list order gave every (query, list) row its own cold start:
+// per-unit prunes and sorts, not the tensor pipe, bounded the scan.)
+
 // Single block: per list, the number of (query, list) pairs m_l, query tiles (padded to an even
 // count so that units 2p, 2p+1 share their item rows), item-run splits and the first unit
-// index; writes the unit list ordered (list, split, tile).
+// index; writes the unit list ordered (list, split, tile) with the lists taken LONGEST FIRST:
+// persistent CTAs take units round-robin, so a descending cost order balances them, and units of
+// one list stay adjacent (concurrent CTAs stream the same item rows through L2).
 __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __restrict__ l_off, int nlist,
                                 int chunk, int* __restrict__ ubase, int* __restrict__ nsl,
                                 int* __restrict__ n_units_out, Unit* __restrict__ units, int max_units) {
-    extern __shared__ int cnt[];  // nlist + 1
+    extern __shared__ int sh_plan[];  // cnt[nlist + 1], perm[nlist]
+    int* cnt = sh_plan;
+    int* perm = sh_plan + nlist + 1;
     for (int l = threadIdx.x; l < nlist; l += blockDim.x) {
         const int m = p_off[l + 1] - p_off[l];
         const int len = l_off[l + 1] - l_off[l];
@@ -239,11 +254,21 @@ __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __rest
         const int ns = (m > 0 && len > 0) ? (len + chunk - 1) / chunk : 0;
         nsl[l] = ns;
         cnt[l] = tiles2 * ns;
+        int rank = l;
+        if (nlist <= 2048) {  // rank sort by list length, descending (ties: list id)
+            rank = 0;
+            for (int o = 0; o < nlist; o++) {
+                const int lo = l_off[o + 1] - l_off[o];
+                rank += (lo > len || (lo == len && o < l)) ? 1 : 0;
+            }
+        }
+        perm[rank] = l;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
-        for (int l = 0; l < nlist; l++) {
+        for (int r = 0; r < nlist; r++) {
+            const int l = perm[r];
             const int t = cnt[l];
             cnt[l] = run;
             run += t;
@@ -261,24 +286,25 @@ __global__ void ivf_plan_kernel(const int* __restrict__ p_off, const int* __rest
         const int tiles = (m + UNIT_ROWS - 1) / UNIT_ROWS;
         const int tiles2 = (tiles + 1) & ~1;
         int u = cnt[l];
-        for (int s = 0; s < ns; s++)
+        for (int sp = 0; sp < ns; sp++)
             for (int t = 0; t < tiles2; t++, u++) {
                 if (u >= max_units) continue;
                 Unit un;
                 un.a_row0 = t < tiles ? p_off[l] + t * UNIT_ROWS : 0;
                 un.a_rows = t < tiles ? min(UNIT_ROWS, m - t * UNIT_ROWS) : 0;
-                un.b_row0 = l_off[l] + s * chunk;
-                un.b_rows = min(chunk, len - s * chunk);
+                un.b_row0 = l_off[l] + sp * chunk;
+                un.b_rows = min(chunk, len - sp * chunk);
                 units[u] = un;
             }
     }
 }
 
-// src[(q*nprobe + j)*maxsplit + s] = partial row of pair (q, j) in split s, or -1.
+// Pair e = q*ncols + j of a phase (list coarse[e]): src[q*S + s_off + (j*maxsplit + sp)*wgs + g] =
+// partial row of the pair in split sp, warpgroup g (prow_base + local partial row), or -1.
 __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __restrict__ pos_of,
                                const int* __restrict__ p_off, const int* __restrict__ ubase,
-                               const int* __restrict__ nsl, int nlist, int64_t npairs, int maxsplit, int wgs,
-                               int* __restrict__ src) {
+                               const int* __restrict__ nsl, int nlist, int64_t npairs, int ncols, int maxsplit,
+                               int wgs, int S, int s_off, int prow_base, int* __restrict__ src) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < npairs;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int pos = pos_of[e];
@@ -292,14 +318,31 @@ __global__ void ivf_src_kernel(const int64_t* __restrict__ coarse, const int* __
             u0 = ubase[l] + i / UNIT_ROWS;
             r = i % UNIT_ROWS;
         }
+        const int64_t q = e / ncols;
+        const int j = (int)(e - q * ncols);
+        int* dst = src + q * S + s_off + (int64_t)j * maxsplit * wgs;
         // partial row of (unit u, warpgroup g, row r) = (u*wgs + g)*128 + r
-        for (int s = 0; s < maxsplit; s++)
+        for (int sp = 0; sp < maxsplit; sp++)
             for (int g = 0; g < wgs; g++)
-                src[(e * maxsplit + s) * wgs + g] = (s < ns) ? ((u0 + s * tiles2) * wgs + g) * UNIT_ROWS + r : -1;
+                dst[sp * wgs + g] = (sp < ns) ? prow_base + ((u0 + sp * tiles2) * wgs + g) * UNIT_ROWS + r : -1;
     }
 }
 
-// item rows per unit inside one list: long runs amortise the per-unit prunes and sorts (sweep on config 2:
+// coarse i64[nq, nprobe] -> ca[nq] (rank 0) and cb[nq, nprobe - 1] (the rest)
+__global__ void ivf_split_coarse_kernel(const int64_t* __restrict__ coarse, int64_t nq, int nprobe,
+                                        int64_t* __restrict__ ca, int64_t* __restrict__ cb) {
+    const int64_t total = nq * nprobe;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = t / nprobe;
+        const int j = (int)(t - q * nprobe);
+        if (j == 0)
+            ca[q] = coarse[t];
+        else
+            cb[q * (nprobe - 1) + (j - 1)] = coarse[t];
+    }
+}
+
+// item rows per unit inside one list: long runs amortise the per-unit work (sweep on config 2:
 // 4,096 -> 40.4 ms, 8,192 -> 36.2, 16,384 -> 35.4, 32,768 -> 33.8); NRB_IVF_CHUNK overrides
 static int ivf_chunk() {
     const char* e = getenv("NRB_IVF_CHUNK");  // read per call: tests force small runs to cover split lists
@@ -307,34 +350,69 @@ static int ivf_chunk() {
     return v >= 256 ? (v + 255) / 256 * 256 : 32768;
 }
 
-struct IvfPlan {
+constexpr int IVF_MAX_SOURCES = 256;  // partial rows per query the sorted merge can take (select_merge_kernel<8>)
+
+struct IvfPhase {
+    int ncols;  // lists of every query handled by this phase
     int64_t npairs;
-    int maxsplit, max_units, grid, wgs;
+    int max_units, grid, s_off, prow_base;
+};
+
+struct IvfPlan {
+    int chunk, maxsplit, wgs, S, nph;
+    IvfPhase ph[2];
+    int64_t total_units;
 };
 
 static IvfPlan plan_ivf(int64_t nq, int nprobe, int nlist, int max_list_len, int path) {
     IvfPlan p;
-    p.npairs = nq * nprobe;
-    p.maxsplit = (max_list_len + ivf_chunk() - 1) / ivf_chunk();
-    if (p.maxsplit < 1) p.maxsplit = 1;
-    int64_t mu = (p.npairs / UNIT_ROWS + 2 * (int64_t)nlist) * p.maxsplit;
-    p.max_units = (int)mu;
     p.wgs = path == NRB_PATH_SIMT ? 1 : 2;
-    p.grid = path == NRB_PATH_SIMT ? simt_grid(p.max_units) : tc_grid(p.max_units);
+    // long lists are cut into runs of `chunk` rows; the run length grows until the partial rows of a
+    // query (nprobe x splits x warpgroups) fit the merge (a 10M-row catalog with one list of 70k rows
+    // and nprobe 64 used to be refused)
+    p.chunk = ivf_chunk();
+    p.maxsplit = 1;
+    for (;;) {
+        p.maxsplit = (max_list_len + p.chunk - 1) / p.chunk;
+        if (p.maxsplit < 1) p.maxsplit = 1;
+        if ((int64_t)nprobe * p.maxsplit * p.wgs <= IVF_MAX_SOURCES || p.maxsplit == 1) break;
+        p.chunk *= 2;
+    }
+    p.S = nprobe * p.maxsplit * p.wgs;
+    // the SIMT kernels keep no shared running bounds: one phase
+    p.nph = (nprobe > 1 && path != NRB_PATH_SIMT && !getenv("NRB_IVF_ONE_PHASE")) ? 2 : 1;
+    p.total_units = 0;
+    for (int i = 0; i < p.nph; i++) {
+        IvfPhase& f = p.ph[i];
+        f.ncols = p.nph == 1 ? nprobe : (i == 0 ? 1 : nprobe - 1);
+        f.npairs = nq * f.ncols;
+        f.max_units = (int)((f.npairs / UNIT_ROWS + 2 * (int64_t)nlist) * p.maxsplit);
+        f.grid = path == NRB_PATH_SIMT ? simt_grid(f.max_units) : tc_grid(f.max_units);
+        f.s_off = i == 0 ? 0 : p.ph[0].ncols * p.maxsplit * p.wgs;
+        f.prow_base = (int)(p.total_units * p.wgs * UNIT_ROWS);
+        p.total_units += f.max_units;
+    }
     return p;
 }
 
-struct IvfWs {
+struct IvfPhaseWs {
     void* cs;
     size_t cs_bytes;
-    int *p_off, *order, *pos_of, *ubase, *nsl, *n_units, *src;
-    unsigned* gthr;
+    int64_t* coarse;  // this phase's columns of the coarse assignment, contiguous (two phases only)
+    int *p_off, *order, *pos_of, *ubase, *nsl, *n_units;
     Unit* units;
-    float *g_raw, *g_hi, *g_lo, *g_norms, *part_key;
+    float *g_raw, *g_hi, *g_lo, *g_norms;
     void* g_h16;     // fp16 filter: regrouped scaled fp16 query rows ...
     float* g_scale;  // ... and their per-row scales
+};
+
+struct IvfWs {
+    IvfPhaseWs ph[2];
+    int* src;
+    unsigned* gthr;
+    float* part_key;
+    int *part_idx, *part_cnt;
     int *flags, *flag_list, *flag_count;
-    int* part_idx;
     void* scratch;
     size_t scratch_bytes, total;
 };
@@ -342,39 +420,49 @@ struct IvfWs {
 static IvfWs carve_ivf(void* ws, const IvfPlan& p, int nlist, int k, int kp, int path, int64_t nq) {
     Carver c(ws);
     IvfWs w;
-    w.gthr = path == NRB_PATH_SIMT ? nullptr : c.take<unsigned>(nq);
-    w.cs_bytes = counting_sort_ws(p.npairs, nlist);
-    w.cs = c.take<char>(w.cs_bytes);
-    w.p_off = c.take<int>(nlist + 2);
-    w.order = c.take<int>(p.npairs);
-    w.pos_of = c.take<int>(p.npairs);
-    w.ubase = c.take<int>(nlist + 1);
-    w.nsl = c.take<int>(nlist);
-    w.n_units = c.take<int>(1);
-    w.src = c.take<int>((size_t)p.npairs * p.maxsplit * p.wgs);
-    w.units = c.take<Unit>(p.max_units);
-    const size_t plane = (size_t)(p.npairs + UNIT_ROWS) * kp;
     const bool filt = path == NRB_PATH_TC16;
     const int pw = filt ? tc1_pw(k) : k;  // partial row width
-    w.g_raw = w.g_hi = w.g_lo = w.g_scale = nullptr;
-    w.g_h16 = nullptr;
-    w.flags = w.flag_list = w.flag_count = nullptr;
-    if (path == NRB_PATH_SIMT) {
-        w.g_raw = c.take<float>(plane);
-    } else if (filt) {
-        w.g_h16 = c.take<uint16_t>(plane);
-        w.g_scale = c.take<float>(p.npairs + UNIT_ROWS);
+    w.gthr = path == NRB_PATH_SIMT ? nullptr : c.take<unsigned>(nq);
+    w.src = c.take<int>((size_t)nq * p.S);
+    int max_grid = 0;
+    for (int i = 0; i < p.nph; i++) {
+        const IvfPhase& f = p.ph[i];
+        IvfPhaseWs& v = w.ph[i];
+        v.cs_bytes = counting_sort_ws(f.npairs, nlist);
+        v.cs = c.take<char>(v.cs_bytes);
+        v.coarse = p.nph > 1 ? c.take<int64_t>(f.npairs) : nullptr;
+        v.p_off = c.take<int>(nlist + 2);
+        v.order = c.take<int>(f.npairs);
+        v.pos_of = c.take<int>(f.npairs);
+        v.ubase = c.take<int>(nlist + 1);
+        v.nsl = c.take<int>(nlist);
+        v.n_units = c.take<int>(1);
+        v.units = c.take<Unit>(f.max_units);
+        const size_t plane = (size_t)(f.npairs + UNIT_ROWS) * kp;
+        v.g_raw = v.g_hi = v.g_lo = v.g_scale = nullptr;
+        v.g_h16 = nullptr;
+        if (path == NRB_PATH_SIMT) {
+            v.g_raw = c.take<float>(plane);
+        } else if (filt) {
+            v.g_h16 = c.take<uint16_t>(plane);
+            v.g_scale = c.take<float>(f.npairs + UNIT_ROWS);
+        } else {
+            v.g_hi = c.take<float>(plane);
+            v.g_lo = c.take<float>(plane);
+        }
+        v.g_norms = c.take<float>(f.npairs + UNIT_ROWS);
+        max_grid = f.grid > max_grid ? f.grid : max_grid;
+    }
+    w.flags = w.flag_list = w.flag_count = w.part_cnt = nullptr;
+    if (filt) {
+        w.part_cnt = c.take<int>((size_t)p.total_units * p.wgs * UNIT_ROWS);
         w.flags = c.take<int>(nq);
         w.flag_list = c.take<int>(nq);
         w.flag_count = c.take<int>(1);
-    } else {
-        w.g_hi = c.take<float>(plane);
-        w.g_lo = c.take<float>(plane);
     }
-    w.g_norms = c.take<float>(p.npairs + UNIT_ROWS);
-    w.part_key = c.take<float>((size_t)p.max_units * p.wgs * UNIT_ROWS * pw);
-    w.part_idx = c.take<int>((size_t)p.max_units * p.wgs * UNIT_ROWS * pw);
-    w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(p.grid) : tc_scratch_bytes(p.grid);
+    w.part_key = c.take<float>((size_t)p.total_units * p.wgs * UNIT_ROWS * pw);
+    w.part_idx = c.take<int>((size_t)p.total_units * p.wgs * UNIT_ROWS * pw);
+    w.scratch_bytes = path == NRB_PATH_SIMT ? simt_scratch_bytes(max_grid) : tc_scratch_bytes(max_grid);
     w.scratch = c.take<char>(w.scratch_bytes);
     w.total = c.off;
     return w;
@@ -508,11 +596,11 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     {
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
-                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, nullptr, 1,
+                                 w.part_idx, w.part_cnt, w.flags, w.scratch, w.scratch_bytes, w.gthr, nullptr, 1,
                                  path == NRB_PATH_TC16, p.single, st);
     }
     if (rc) return rc;
-    if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
+    if ((rc = launch_gather_refine(w.part_key, w.part_idx, w.part_cnt, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
                                    id_base, nullptr, w.flags, D, I, st))) return rc;
     if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
     int nflag = 0;
@@ -591,15 +679,14 @@ extern "C" int nrb_plan_flat_describe(int64_t nq, int64_t nb, int32_t k, int32_t
 extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k, int32_t kp,
                                            int32_t nlist, int32_t max_list_len) {
     if (nq <= 0 || nprobe <= 0 || k <= 0) return 256;
-    IvfPlan p1 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_TC);
-    IvfPlan p2 = plan_ivf(nq, nprobe, nlist, max_list_len, NRB_PATH_SIMT);
-    size_t a = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC, nq).total;
-    size_t b = carve_ivf(nullptr, p2, nlist, k, kp, NRB_PATH_SIMT, nq).total;
-    if (tc1_k_ok(k)) {
-        const size_t f = carve_ivf(nullptr, p1, nlist, k, kp, NRB_PATH_TC16, nq).total;
-        a = f > a ? f : a;
+    size_t best = 0;
+    for (int path : {NRB_PATH_TC, NRB_PATH_SIMT, NRB_PATH_TC16}) {
+        if (path == NRB_PATH_TC16 && !tc1_k_ok(k)) continue;
+        const IvfPlan p = plan_ivf(nq, nprobe, nlist, max_list_len, path);
+        const size_t t = carve_ivf(nullptr, p, nlist, k, kp, path, nq).total;
+        best = t > best ? t : best;
     }
-    return (a > b ? a : b) + 256;
+    return best + 256;
 }
 
 namespace nrb {
@@ -623,82 +710,95 @@ static int ivf_search_impl(const nrb_matrix* q, const nrb_matrix* lists, const i
     int rc;
     const bool filt = path == NRB_PATH_TC16;
     const IvfPlan p = plan_ivf(q->n, nprobe, nlist, max_list_len, path);
-    NRB_REQUIRE((int64_t)nprobe * p.maxsplit * p.wgs <= 256, "ivf_search: nprobe*splits = %d > 256 merge sources", nprobe * p.maxsplit * p.wgs);
+    NRB_REQUIRE(filt || p.S <= IVF_MAX_SOURCES, "ivf_search: nprobe*splits = %d > %d merge sources", p.S, IVF_MAX_SOURCES);
     const IvfWs w = carve_ivf(workspace, p, nlist, k, q->kp, path, q->n);
     if (!workspace || workspace_bytes < w.total) {
         set_error("ivf_search: workspace %zu < %zu bytes", workspace_bytes, w.total);
         return NRB_ERR_WORKSPACE;
     }
-    // 1. group (query, list) pairs by list (stable): p_off, order (position -> pair), pos_of
-    NRB_CUDA_CHECK(cudaMemsetAsync(w.order, 0, (size_t)p.npairs * sizeof(int), st));
-    if ((rc = launch_counting_sort_i64(coarse, p.npairs, nlist, w.p_off, w.order, w.pos_of, w.cs, w.cs_bytes, st))) return rc;
-    // 2. units + src table, all on the device
-    const size_t sh = (size_t)(nlist + 1) * sizeof(int);
-    ivf_plan_kernel<<<1, 512, sh, st>>>(w.p_off, offsets, nlist, ivf_chunk(), w.ubase, w.nsl, w.n_units, w.units, p.max_units);
-    NRB_LAUNCH_CHECK();
-    {
-        int64_t blocks = (p.npairs + 255) / 256;
+    if (metric == NRB_METRIC_L2 || filt) NRB_REQUIRE(q->norms && lists->norms, "ivf_search: norms required");
+    if (p.nph > 1) {
+        int64_t blocks = (q->n * nprobe + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        ivf_src_kernel<<<(unsigned)blocks, 256, 0, st>>>(coarse, w.pos_of, w.p_off, w.ubase, w.nsl, nlist, p.npairs, p.maxsplit, p.wgs, w.src);
+        ivf_split_coarse_kernel<<<(unsigned)blocks, 256, 0, st>>>(coarse, q->n, nprobe, w.ph[0].coarse, w.ph[1].coarse);
         NRB_LAUNCH_CHECK();
     }
-    // 3. query rows in group order
-    nrb_matrix g;
-    memset(&g, 0, sizeof(g));
-    g.n = p.npairs;
-    g.d = q->d;
-    g.kp = q->kp;
-    g.raw = w.g_raw;
-    g.hi = w.g_hi;
-    g.lo = w.g_lo;
-    if (path == NRB_PATH_SIMT) {
-        NRB_REQUIRE(q->raw, "ivf_search: raw plane required");
-        if ((rc = launch_gather_rows(q->raw, q->kp, w.order, nprobe, p.npairs, w.g_raw, st))) return rc;
-    } else if (filt) {
-        // fp16 rows are kp/2 floats wide; their per-row scales and norms travel with them
-        if ((rc = launch_gather_rows((const float*)q->h16, q->kp / 2, w.order, nprobe, p.npairs, (float*)w.g_h16, st))) return rc;
-        if ((rc = launch_gather_scalar(q->h16_row_scale, w.order, nprobe, p.npairs, w.g_scale, st))) return rc;
-        g.h16 = w.g_h16;
-        g.h16_row_scale = w.g_scale;
-    } else {
-        NRB_REQUIRE(q->hi && q->lo, "ivf_search: hi/lo planes required");
-        if ((rc = launch_gather_rows(q->hi, q->kp, w.order, nprobe, p.npairs, w.g_hi, st))) return rc;
-        if ((rc = launch_gather_rows(q->lo, q->kp, w.order, nprobe, p.npairs, w.g_lo, st))) return rc;
-    }
-    if (metric == NRB_METRIC_L2 || filt) {
-        NRB_REQUIRE(q->norms && lists->norms, "ivf_search: norms required");
-        if ((rc = launch_gather_scalar(q->norms, w.order, nprobe, p.npairs, w.g_norms, st))) return rc;
-        g.norms = w.g_norms;
-    }
-    // 4. distance + selection over the units, 5. merge per query
-    const int S = nprobe * p.maxsplit * p.wgs;
     if (path != NRB_PATH_SIMT) NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
-    if (!filt) {
-        {
-            ProfScope prof(st);
-            if (path == NRB_PATH_SIMT)
-                rc = launch_topk_simt_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch, w.scratch_bytes, st);
-            else
-                // all nprobe units of a query share one running bound: row p of the regrouped plane is
-                // pair order[p], i.e. query order[p] / nprobe
-                rc = launch_topk_tc_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, w.part_key, w.part_idx, w.scratch,
-                                        w.scratch_bytes, w.gthr, w.order, nprobe, st);
-        }
-        if (rc) return rc;
-        return launch_select(w.part_key, w.part_idx, w.src, S, q->n, k, metric, ids, 0, D, I, st);
-    }
-    // ---- fp16 filter over the lists + exact refine, then 3xTF32 for whatever was flagged
-    const int pw = tc1_pw(k);
+    if (filt) NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
+    const int pw = filt ? tc1_pw(k) : k;
     const float eps_xmax = TC1_EPS * lists->max_norm;
-    NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
-    {
-        ProfScope prof(st);
-        rc = launch_topk_tc1_dev(&g, lists, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
-                                 w.part_idx, w.flags, w.scratch, w.scratch_bytes, w.gthr, w.order, nprobe, 1, 0, st);
+    nrb_matrix g[2];
+    // ---- per phase: grouping, unit list, src table, regrouped query rows (all on the device)
+    for (int i = 0; i < p.nph; i++) {
+        const IvfPhase& f = p.ph[i];
+        const IvfPhaseWs& v = w.ph[i];
+        const int64_t* co = p.nph > 1 ? v.coarse : coarse;
+        // 1. group (query, list) pairs by list (stable): p_off, order (position -> pair), pos_of
+        NRB_CUDA_CHECK(cudaMemsetAsync(v.order, 0, (size_t)f.npairs * sizeof(int), st));
+        if ((rc = launch_counting_sort_i64(co, f.npairs, nlist, v.p_off, v.order, v.pos_of, v.cs, v.cs_bytes, st))) return rc;
+        // 2. units + src table
+        const size_t sh = (size_t)(2 * nlist + 1) * sizeof(int);
+        NRB_REQUIRE(sh <= 48 * 1024, "ivf_search: too many lists (%d)", nlist);
+        ivf_plan_kernel<<<1, 512, sh, st>>>(v.p_off, offsets, nlist, p.chunk, v.ubase, v.nsl, v.n_units, v.units, f.max_units);
+        NRB_LAUNCH_CHECK();
+        {
+            int64_t blocks = (f.npairs + 255) / 256;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            ivf_src_kernel<<<(unsigned)blocks, 256, 0, st>>>(co, v.pos_of, v.p_off, v.ubase, v.nsl, nlist, f.npairs, f.ncols,
+                                                             p.maxsplit, p.wgs, p.S, f.s_off, f.prow_base, w.src);
+            NRB_LAUNCH_CHECK();
+        }
+        // 3. query rows in group order: row p of the regrouped plane is pair order[p], i.e. query order[p] / ncols
+        nrb_matrix& gm = g[i];
+        memset(&gm, 0, sizeof(gm));
+        gm.n = f.npairs;
+        gm.d = q->d;
+        gm.kp = q->kp;
+        gm.raw = v.g_raw;
+        gm.hi = v.g_hi;
+        gm.lo = v.g_lo;
+        if (path == NRB_PATH_SIMT) {
+            NRB_REQUIRE(q->raw, "ivf_search: raw plane required");
+            if ((rc = launch_gather_rows(q->raw, q->kp, v.order, f.ncols, f.npairs, v.g_raw, st))) return rc;
+        } else if (filt) {
+            // fp16 rows are kp/2 floats wide; their per-row scales and norms travel with them
+            if ((rc = launch_gather_rows((const float*)q->h16, q->kp / 2, v.order, f.ncols, f.npairs, (float*)v.g_h16, st))) return rc;
+            if ((rc = launch_gather_scalar(q->h16_row_scale, v.order, f.ncols, f.npairs, v.g_scale, st))) return rc;
+            gm.h16 = v.g_h16;
+            gm.h16_row_scale = v.g_scale;
+        } else {
+            NRB_REQUIRE(q->hi && q->lo, "ivf_search: hi/lo planes required");
+            if ((rc = launch_gather_rows(q->hi, q->kp, v.order, f.ncols, f.npairs, v.g_hi, st))) return rc;
+            if ((rc = launch_gather_rows(q->lo, q->kp, v.order, f.ncols, f.npairs, v.g_lo, st))) return rc;
+        }
+        if (metric == NRB_METRIC_L2 || filt) {
+            if ((rc = launch_gather_scalar(q->norms, v.order, f.ncols, f.npairs, v.g_norms, st))) return rc;
+            gm.norms = v.g_norms;
+        }
     }
-    if (rc) return rc;
-    if ((rc = launch_select_refine(w.part_key, w.part_idx, w.src, S, q->n, k, pw, metric, q, lists, eps_xmax, 0, ids,
-                                   w.flags, D, I, st))) return rc;
+    // ---- 4. distance + selection over the units, phase A then phase B (which starts from A's bounds)
+    for (int i = 0; i < p.nph; i++) {
+        const IvfPhase& f = p.ph[i];
+        const IvfPhaseWs& v = w.ph[i];
+        const size_t po = (size_t)f.prow_base * pw;
+        ProfScope prof(st);
+        if (path == NRB_PATH_SIMT)
+            rc = launch_topk_simt_dev(&g[i], lists, v.units, v.n_units, f.grid, metric, k, w.part_key + po, w.part_idx + po,
+                                      w.scratch, w.scratch_bytes, st);
+        else if (!filt)
+            // all units of a query share one running bound
+            rc = launch_topk_tc_dev(&g[i], lists, v.units, v.n_units, f.grid, metric, k, w.part_key + po, w.part_idx + po,
+                                    w.scratch, w.scratch_bytes, w.gthr, v.order, f.ncols, st);
+        else
+            rc = launch_topk_tc1_dev(&g[i], lists, v.units, v.n_units, f.grid, metric, k, pw, 2.f * eps_xmax, w.part_key + po,
+                                     w.part_idx + po, w.part_cnt + f.prow_base, w.flags, w.scratch, w.scratch_bytes, w.gthr,
+                                     v.order, f.ncols, 1, 0, st);
+        if (rc) return rc;
+    }
+    // ---- 5. per query: merge (sorted partial rows) or gather + exact refine (filter)
+    if (!filt) return launch_select(w.part_key, w.part_idx, w.src, p.S, q->n, k, metric, ids, 0, D, I, st);
+    if ((rc = launch_gather_refine(w.part_key, w.part_idx, w.part_cnt, w.src, p.S, q->n, k, pw, metric, q, lists, eps_xmax,
+                                   0, ids, w.flags, D, I, st))) return rc;
     if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
     int nflag = 0;
     NRB_CUDA_CHECK(cudaMemcpyAsync(&nflag, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));

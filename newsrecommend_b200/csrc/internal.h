@@ -48,7 +48,7 @@ int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
 int tc16_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
-                        float* part_key, int* part_idx, int* row_flags, void* scratch,
+                        float* part_key, int* part_idx, int* part_cnt, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
                         int single, cudaStream_t st);
 
@@ -65,8 +65,10 @@ int launch_topk_simt_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* u
 int launch_select(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
                   int k, int metric, const int64_t* id_map, int64_t id_base, float* D, int64_t* I,
                   cudaStream_t st);
-int launch_select_refine(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
-                         int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
+// filter paths: gathers the unsorted partial rows of every query (part_cnt entries each), cuts at
+// (k-th estimate - margin), rescoring the survivors exactly in fp32 and sorting them
+int launch_gather_refine(const float* part_key, const int* part_idx, const int* part_cnt, const int* src, int S,
+                         int64_t nq, int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
                          int64_t id_base, const int64_t* id_map, int* flags, float* D, int64_t* I, cudaStream_t st);
 int launch_compact_flags(const int* flags, int64_t n, int* list, int* count, cudaStream_t st);
 int launch_scatter_results(const float* Df, const int64_t* If, const int* list, int n, int k, float* D,

@@ -399,42 +399,151 @@ __global__ void shard_merge_kernel(ShardSource S, float* __restrict__ D, int64_t
     }
 }
 
-// Merge + exact refine of the 1xTF32 filter (NRB_PATH_TC1). One warp per query: k-way merge of
-// the partial rows (approximate keys), cut at (k-th approximate key - margin), exact fp32
-// rescoring of the surviving candidates from the raw planes (coalesced float4 row reads, warp
-// reduction), sort by the exact key, write the best k. flags[q] is raised when the candidate
-// slots were exhausted inside the margin or when an exact score disagrees with its estimate by
-// more than the assumed error bound; flagged queries are recomputed by the 3xTF32 kernel.
-template <int MAXL, bool L2>
-__global__ void select_refine_kernel(PartSource S, int64_t nq, int k, const float* __restrict__ q_raw,
-                                     const float* __restrict__ q_norms, const float* __restrict__ b_raw,
-                                     const float* __restrict__ b_norms, int kp, float eps_xmax,
-                                     int64_t id_base, const int64_t* __restrict__ id_map, int* __restrict__ flags,
-                                     float* __restrict__ D, int64_t* __restrict__ I) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Gather + exact refine of the filter paths (NRB_PATH_TC1 / NRB_PATH_TC16). The filter kernels
+// leave, per (unit, warpgroup, query row), an UNSORTED partial row of part_cnt candidates
+// (estimate, idx): everything the unit saw above its running threshold. One warp per query:
+//   1. gather the candidates of all S partial rows of the query into shared memory (keys as
+//      ordered uints), dropping what is below the running cut;
+//   2. bisection on the keys gives a lower bound lb of the k-th best estimate (count(key >= lb)
+//      in [k, k+3]); cut = lb - margin; the survivors (key >= cut) provably contain the true
+//      top-k (|estimate - score| <= margin / 2 for every item);
+//   3. exact fp32 rescoring of the survivors from the raw planes (coalesced float4 row reads +
+//      warp reduction), bitonic sort by (exact key, idx), write the best k.
+// When the staging buffer fills up mid-gather, step 2 runs early and raises the cut. flags[q] is
+// raised when more than 128 candidates survive, the buffer overflows even after a reduction, or an
+// exact score disagrees with its estimate by more than the assumed error bound; flagged queries
+// are recomputed by the 3xTF32 kernel.
+constexpr int GR_CAP = 512;  // staged candidates per warp
+constexpr int GR_WPB = 4;    // warps (queries) per block
+
+// lower bound of the k-th largest of su[0..n) (ordered uints, n >= k): count(su >= lb) in [k, k+3]
+// or exact
+__device__ __forceinline__ uint32_t warp_kth_bound(const uint32_t* su, int n, int k, int lane) {
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int e = lane; e < n; e += 32) {
+        const uint32_t v = su[e];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    uint32_t lo = mn, hi = mx + 1u;  // invariant: count(>= lo) >= k > count(>= hi)   (hi may wrap to 0 only for NaN payloads; keys are finite or -inf)
+    if (hi == 0u) hi = 0xffffffffu;
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int e = lane; e < n; e += 32) c += (su[e] >= mid) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) {
+            lo = mid;
+            if (c <= k + 3) break;
+        } else {
+            hi = mid;
+        }
+    }
+    return lo;
+}
+
+// keeps the entries with su >= cut_u, in place (order preserved); returns the new count
+__device__ __forceinline__ int warp_compact_ge(uint32_t* su, int* si, int n, uint32_t cut_u, int lane) {
+    const uint32_t lt = (1u << lane) - 1u;
+    int w = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int e = base + lane;
+        const uint32_t v = e < n ? su[e] : 0u;
+        const int id = e < n ? si[e] : -1;
+        const bool keep = e < n && v >= cut_u;
+        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();  // every lane has read its entry of this chunk; writes go to positions <= base + lane
+        if (keep) {
+            const int pos = w + __popc(b & lt);
+            su[pos] = v;
+            si[pos] = id;
+        }
+        w += __popc(b);
+        __syncwarp();
+    }
+    return w;
+}
+
+template <bool L2>
+__global__ void __launch_bounds__(GR_WPB * 32)
+gather_refine_kernel(const float* __restrict__ part_key, const int* __restrict__ part_idx,
+                     const int* __restrict__ part_cnt, const int* __restrict__ src, int S, int pw, int64_t nq, int k,
+                     const float* __restrict__ q_raw, const float* __restrict__ q_norms,
+                     const float* __restrict__ b_raw, const float* __restrict__ b_norms, int kp, float eps_xmax,
+                     int64_t id_base, const int64_t* __restrict__ id_map, int* __restrict__ flags,
+                     float* __restrict__ D, int64_t* __restrict__ I) {
+    __shared__ uint32_t s_key[GR_WPB][GR_CAP];
+    __shared__ int s_idx[GR_WPB][GR_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * GR_WPB + w;
     if (q >= nq) return;
-    const int pw = S.k;
-    uint64_t res[4];
-    warp_kway_merge<MAXL>(S, q, pw, lane, res);
+    uint32_t* su = s_key[w];
+    int* si = s_idx[w];
+    const uint32_t lt = (1u << lane) - 1u;
     const float qn = q_norms[q];
     const float ebound = eps_xmax * sqrtf(qn) * (L2 ? 2.f : 1.f);
     const float margin = 2.f * ebound;
-    float ak = NEG_INF;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        if (i == ((k - 1) >> 5)) ak = cand_key(res[i]);
-    ak = __shfl_sync(0xffffffffu, ak, (k - 1) & 31);
-    const float cut = ak - margin;
-    int nv = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int r = i * 32 + lane;
-        nv += (r < pw && cand_idx(res[i]) >= 0 && (r < k || cand_key(res[i]) > cut)) ? 1 : 0;
+    bool bad = false;
+    int fill = 0;
+    uint32_t cut_u = 0u;  // entries below it are dropped (0 = below everything)
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        const int prow = s < S ? src[q * S + s] : -1;
+        const int c = prow >= 0 ? part_cnt[prow] : 0;
+        unsigned m = __ballot_sync(0xffffffffu, c > 0);
+        while (m) {  // warp-uniform
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int pr = __shfl_sync(0xffffffffu, prow, l);
+            const int cc = __shfl_sync(0xffffffffu, c, l);
+            if (fill + cc > GR_CAP) {  // staging buffer full: raise the cut from what is there
+                if (fill >= k) {
+                    const uint32_t lb = warp_kth_bound(su, fill, k, lane);
+                    const uint32_t nc = ordered_u32(from_ordered_u32(lb) - margin);
+                    cut_u = nc > cut_u ? nc : cut_u;
+                    fill = warp_compact_ge(su, si, fill, cut_u, lane);
+                }
+                if (fill + cc > GR_CAP) {  // still no room (a huge margin set): recompute exactly
+                    bad = true;
+                    break;
+                }
+            }
+            const int64_t o = (int64_t)pr * pw;
+            for (int e0 = 0; e0 < cc; e0 += 32) {
+                const int e = e0 + lane;
+                uint32_t v = 0u;
+                int id = -1;
+                if (e < cc) {
+                    v = ordered_u32(part_key[o + e]);
+                    id = part_idx[o + e];
+                }
+                const bool keep = e < cc && v >= cut_u;
+                const uint32_t b = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int pos = fill + __popc(b & lt);
+                    su[pos] = v;
+                    si[pos] = id;
+                }
+                fill += __popc(b);
+            }
+            __syncwarp();
+        }
+        if (bad) break;
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
-    bool bad = (nv >= pw);  // every slot is inside the margin: more candidates may exist
+    __syncwarp();
+    if (fill > k) {
+        const uint32_t lb = warp_kth_bound(su, fill, k, lane);
+        const uint32_t nc = ordered_u32(from_ordered_u32(lb) - margin);
+        cut_u = nc > cut_u ? nc : cut_u;
+        fill = warp_compact_ge(su, si, fill, cut_u, lane);
+    }
+    int nv = fill;
+    if (nv > 128) {  // more survivors than the exact stage holds
+        bad = true;
+        nv = 128;
+    }
     // query row in registers
     const int w4 = kp >> 2;
     float4 qv[2];
@@ -451,8 +560,8 @@ __global__ void select_refine_kernel(PartSource S, int64_t nq, int k, const floa
         for (int l = 0; l < 32; l++) {
             const int r = i * 32 + l;
             if (r >= nv) break;  // warp-uniform
-            const int idx = __shfl_sync(0xffffffffu, cand_idx(res[i]), l);
-            const float approx = __shfl_sync(0xffffffffu, cand_key(res[i]), l);
+            const int idx = si[r];
+            const float approx = from_ordered_u32(su[r]);
             const float4* xr = reinterpret_cast<const float4*>(b_raw + (int64_t)idx * kp);
             float acc = 0.f;
 #pragma unroll
@@ -614,34 +723,20 @@ int launch_select(const float* part_key, const int* part_idx, const int* src, in
     return NRB_OK;
 }
 
-int launch_select_refine(const float* part_key, const int* part_idx, const int* src, int S, int64_t nq,
-                         int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
+int launch_gather_refine(const float* part_key, const int* part_idx, const int* part_cnt, const int* src, int S,
+                         int64_t nq, int k, int pw, int metric, const nrb_matrix* q, const nrb_matrix* b, float eps_xmax,
                          int64_t id_base, const int64_t* id_map, int* flags, float* D, int64_t* I, cudaStream_t st) {
     if (nq == 0) return NRB_OK;
-    NRB_REQUIRE(S >= 1 && S <= 256 && pw <= 128 && k <= pw && q->kp <= 256, "select_refine: S=%d pw=%d kp=%d", S, pw, q->kp);
-    PartSource ps{part_key, part_idx, src, S, pw};
-    const int wpb = 8;
-    const unsigned blocks = (unsigned)((nq + wpb - 1) / wpb);
-#define NRB_SR(MAXL)                                                                                         \
-    do {                                                                                                     \
-        if (metric == NRB_METRIC_L2)                                                                         \
-            select_refine_kernel<MAXL, true><<<blocks, wpb * 32, 0, st>>>(ps, nq, k, q->raw, q->norms, b->raw, \
-                                                                          b->norms, q->kp, eps_xmax, id_base, \
-                                                                          id_map, flags, D, I);                      \
-        else                                                                                                 \
-            select_refine_kernel<MAXL, false><<<blocks, wpb * 32, 0, st>>>(ps, nq, k, q->raw, q->norms, b->raw, \
-                                                                           b->norms, q->kp, eps_xmax, id_base, \
-                                                                           id_map, flags, D, I);                     \
-    } while (0)
-    if (S <= 32)
-        NRB_SR(1);
-    else if (S <= 64)
-        NRB_SR(2);
-    else if (S <= 128)
-        NRB_SR(4);
+    NRB_REQUIRE(S >= 1 && pw <= 128 && k <= pw && q->kp <= 256, "gather_refine: S=%d pw=%d kp=%d", S, pw, q->kp);
+    const unsigned blocks = (unsigned)((nq + GR_WPB - 1) / GR_WPB);
+    if (metric == NRB_METRIC_L2)
+        gather_refine_kernel<true><<<blocks, GR_WPB * 32, 0, st>>>(part_key, part_idx, part_cnt, src, S, pw, nq, k, q->raw,
+                                                                    q->norms, b->raw, b->norms, q->kp, eps_xmax, id_base,
+                                                                    id_map, flags, D, I);
     else
-        NRB_SR(8);
-#undef NRB_SR
+        gather_refine_kernel<false><<<blocks, GR_WPB * 32, 0, st>>>(part_key, part_idx, part_cnt, src, S, pw, nq, k, q->raw,
+                                                                     q->norms, b->raw, b->norms, q->kp, eps_xmax, id_base,
+                                                                     id_map, flags, D, I);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

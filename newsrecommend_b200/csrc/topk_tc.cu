@@ -319,6 +319,40 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
     }
 }
 
+// Unit finished, filter kernels: the warp's 32 rows go to the unit's partial rows UNSORTED (`pw`
+// slots per row, part_cnt[row] of them used). The refine stage gathers every partial row of a
+// query, finds the k-th best estimate by bisection and rescoring the survivors exactly sorts them,
+// so the per-(unit, row) sort of the plain top-k kernels would be wasted work here -- for the short
+// units of an IVF scan it cost more than the unit's MMAs. The caller has already brought every
+// row down to at most pw entries (final union prune) or flagged it.
+__device__ __forceinline__ void epi_unit_end_unsorted(int n, const float* ck, const int* ci, int64_t prow0, int pw,
+                                                      float* part_key, int* part_idx, int* part_cnt, int lane) {
+    part_cnt[prow0 + lane] = n;
+    // rows with more than a few entries: warp-cooperative, coalesced copies
+    unsigned big = __ballot_sync(0xffffffffu, n > 4);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int nn = __shfl_sync(0xffffffffu, n, src);
+        const float* rk = ck + (int64_t)src * CAND_CAP;
+        const int* ri = ci + (int64_t)src * CAND_CAP;
+        const int64_t o = (prow0 + src) * pw;
+        for (int e = lane; e < nn; e += 32) {
+            part_key[o + e] = rk[e];
+            part_idx[o + e] = ri[e];
+        }
+    }
+    if (n <= 4) {  // the common case of a hot row: a handful of entries, copied by the row's own lane
+        const float* rk = ck + (int64_t)lane * CAND_CAP;
+        const int* ri = ci + (int64_t)lane * CAND_CAP;
+        const int64_t o = (prow0 + lane) * pw;
+        for (int e = 0; e < n; e++) {
+            part_key[o + e] = rk[e];
+            part_idx[o + e] = ri[e];
+        }
+    }
+}
+
 // Scheduled prune of 16 query rows by one warp, on the UNION of the two warpgroups' buffers of
 // each row (xs->cnt / thr / margin were published by both warps of the lane quarter):
 //   * a lower bound lb of the k-th best key of the union is found by bisection on the ordered-uint
@@ -340,6 +374,10 @@ constexpr int UT_ROWS = NRB_UT_ROWS;  // rows of a scheduled prune in flight tog
 // a row pair is pruned only once min_new new candidates have arrived in one of its rows -- rows
 // whose threshold was already hot when the unit started are left alone and the scheduled prune
 // costs them nothing but the barrier (IVF scan -5 %; the flat search prunes every row anyway).
+// min_new < 0 (unit end, unsorted partial output): a row pair is pruned only if one of its rows can
+// still yield something -- a buffer that does not fit the partial row (more than keep_max entries),
+// or at least k candidates in the union with some of them new since the row's last prune (a
+// tighter bound of the k-th for the query's other units, and fewer candidates for the refine).
 __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, int* ci_cta, int quad, int half,
                                                 int k, int keep_max, int min_new) {
     constexpr int NB = UT_ROWS;  // rows in flight: their loads and reduction chains overlap
@@ -351,11 +389,18 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
         float *kA[NB], *kB[NB];
         int *iA[NB], *iB[NB];
         float floor_t[NB], mg[NB];
-        if (min_new > 0) {
+        if (min_new != 0) {
             const int r0 = quad * 32 + half * 16 + NB * it;
             bool quiet = true;
 #pragma unroll
-            for (int b = 0; b < NB; b++) quiet = quiet && (xs->fresh[0][r0 + b] + xs->fresh[1][r0 + b] < min_new);
+            for (int b = 0; b < NB; b++) {
+                const int c0 = xs->cnt[0][r0 + b], c1 = xs->cnt[1][r0 + b];
+                const int fr = xs->fresh[0][r0 + b] + xs->fresh[1][r0 + b];
+                if (min_new > 0)
+                    quiet = quiet && (fr < min_new);
+                else
+                    quiet = quiet && !(c0 > keep_max || c1 > keep_max || (c0 + c1 >= k && fr > 0));
+            }
             if (quiet) {
                 if (lane < NB) xs->done[r0 + lane] = 0;
                 continue;  // warp-uniform
@@ -531,6 +576,7 @@ struct EpiArgs {
     int64_t a_total, b_total;
     float* part_key;
     int* part_idx;
+    int* part_cnt;  // filter kernels: partial rows are UNSORTED, part_cnt[partial row] entries each (see epi_unit_end_unsorted)
     int* row_flags;
     float* cand_key_buf;
     int* cand_idx_buf;
@@ -678,8 +724,31 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 }
             }
         }
-        epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
-                     A.part_idx, lane);
+        if (NEED_QN) {
+            // final union prune (rows that need one only), then the rows leave unsorted
+            xs->cnt[wg][row] = st.cnt;
+            xs->fresh[wg][row] = st.cnt - st.base;
+            xs->thr[wg][row] = st.thr;
+            if (wg == 0) xs->margin[row] = st.margin;
+            ptx::named_bar_sync(3 + quad, 64);
+            union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
+                               A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw, -1);
+            ptx::named_bar_sync(3 + quad, 64);
+            if (xs->done[row]) {
+                st.cnt = xs->cnt[wg][row];
+                const uint32_t lbu = xs->lb[row];
+                if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
+            }
+            if (st.cnt > A.pw) {  // the margin set does not fit: the query is recomputed by the exact path
+                st.flag = 1;
+                st.cnt = A.pw;
+            }
+            epi_unit_end_unsorted(live ? st.cnt : 0, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.pw,
+                                  A.part_key, A.part_idx, A.part_cnt, lane);
+        } else {
+            epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
+                         A.part_idx, lane);
+        }
         if (NEED_QN && st.flag && live) A.row_flags[A.row_map ? A.row_map[ar] / A.row_div : (int)ar] = 1;  // per QUERY
     }
 }
@@ -807,7 +876,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ selection epilogue
         ptx::setmaxnreg_inc<232>();
-        EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
+        EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
                    cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, 0);
     }
@@ -947,7 +1016,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     } else if (warp >= EPI_WARP0) {
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
         ptx::setmaxnreg_inc<232>();
-        EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr,
+        EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
                    cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
@@ -1023,7 +1092,8 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
                                          int k, int pw, float margin_scale, const float* __restrict__ a_norms,
                                          const float* __restrict__ b_norms, int64_t a_total, int64_t b_total,
                                          float* __restrict__ part_key, int* __restrict__ part_idx,
-                                         int* __restrict__ row_flags, float* __restrict__ cand_key_buf,
+                                         int* __restrict__ part_cnt, int* __restrict__ row_flags,
+                                         float* __restrict__ cand_key_buf,
                                          int* __restrict__ cand_idx_buf, unsigned* __restrict__ gthr,
                                          const float* __restrict__ a_row_scale, float b_scale,
                                          const int* __restrict__ row_map, int row_div) {
@@ -1205,7 +1275,7 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
         // ------------------------------------------------------------------ filter epilogue (every CTA)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale};
+                   part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale};
         epilogue_run<L2, PAIR, true>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
@@ -1229,12 +1299,13 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
     const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_bh,                         \
         const Unit *__restrict__ units, const int *__restrict__ n_units_p, int nkc, int k, int pw, float margin_scale, \
         const float *__restrict__ a_norms, const float *__restrict__ b_norms, int64_t a_total, int64_t b_total,    \
-        float *__restrict__ part_key, int *__restrict__ part_idx, int *__restrict__ row_flags,                     \
+        float *__restrict__ part_key, int *__restrict__ part_idx, int *__restrict__ part_cnt,                      \
+        int *__restrict__ row_flags,                                                                               \
         float *__restrict__ cand_key_buf, int *__restrict__ cand_idx_buf, unsigned *__restrict__ gthr,             \
         const float *__restrict__ a_row_scale, float b_scale, const int *__restrict__ row_map, int row_div
 #define NRB_TC3_ARGS                                                                                                  \
     map_ah, map_bh, units, n_units_p, nkc, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx, \
-        row_flags, cand_key_buf, cand_idx_buf, gthr, a_row_scale, b_scale, row_map, row_div
+        part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, a_row_scale, b_scale, row_map, row_div
 
 template <bool L2, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) topk_tc3_kernel(NRB_TC3_PARAMS) {
@@ -1404,9 +1475,10 @@ int tc16_eligible(const nrb_matrix* a, const nrb_matrix* b, int k) {
 
 int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* units,
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
-                        float* part_key, int* part_idx, int* row_flags, void* scratch,
+                        float* part_key, int* part_idx, int* part_cnt, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
                         int single, cudaStream_t st) {
+    NRB_REQUIRE(part_cnt, "tc1: part_cnt required (the filter kernels write unsorted partial rows)");
     NRB_REQUIRE(!single || f16, "tc1: the single-CTA form exists for the fp16 planes only");
     // what the KERNEL reads (the raw planes are the refine stage's business: *_eligible)
     if (f16)
@@ -1441,7 +1513,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                                             (int)v3_smem<F16V>()));                                                 \
         topk_tc3_kernel<L2V, F16V><<<grid, NUM_THREADS, v3_smem<F16V>(), st>>>(mah, mbh, units, n_units_dev, nkc, k, pw,      \
                                                                       margin_scale, a->norms, b->norms, a->n, b->n, \
-                                                                      part_key, part_idx, row_flags, ck, ci, gthr,  \
+                                                                      part_key, part_idx, part_cnt, row_flags, ck, ci, gthr,  \
                                                                       ars, bsc, row_map, row_div);                  \
     } while (0)
     if (single) {
@@ -1450,12 +1522,12 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
             NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM1));
             topk_tc3s_kernel<true><<<grid, NUM_THREADS, SM1, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
                                                                    a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                   row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
+                                                                   part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
         } else {
             NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM1));
             topk_tc3s_kernel<false><<<grid, NUM_THREADS, SM1, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
                                                                     a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                    row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
+                                                                    part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
         }
     } else if (metric == NRB_METRIC_L2) {
         if (f16)

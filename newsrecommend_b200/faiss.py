@@ -29,6 +29,7 @@ __all__ = [
     "IndexIVFFlat", "Clustering", "ClusteringParameters", "vector_float_to_array", "normalize_L2",
 ]
 
+_FLT_MAX = 3.4028234663852886e38
 IVF_QUERY_BATCH = 131072  # queries per nrb_ivf_search call (bounds the regrouped query planes and partial rows: ~8 GB at nprobe 16, k 50)
 
 
@@ -284,6 +285,11 @@ class IndexFlat:
         return self._xb
 
     def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0):
+        if self.ntotal == 0:
+            # faiss on an empty index: I = -1, D = +/-FLT_MAX (also what an empty catalog shard returns)
+            D = torch.full((q.n, k), _FLT_MAX if self.metric_type == METRIC_L2 else -_FLT_MAX,
+                           dtype=torch.float32, device=q.device)
+            return D, torch.full((q.n, k), -1, dtype=torch.int64, device=q.device)
         return _search_flat_dev(q, self._packed(), self.metric_type, k, id_base, self.path)
 
     def search(self, x, k: int, D=None, I=None):

@@ -142,8 +142,11 @@ def finalize_candidates(offsets, candidates, ground_truth, cap=None, seed=0):
         g = torch.Generator(device=off.device).manual_seed(seed)
         lens = off[1:] - off[:-1]
         row = torch.repeat_interleave(torch.arange(nu, device=off.device), lens)
-        key = torch.rand(cand.shape[0], generator=g, device=off.device) + row  # random order inside each row
-        perm = torch.argsort(key)
+        # random order inside each row: shuffle everything, then a STABLE sort by row (the row must
+        # not be folded into a float32 key -- at row ~50,000 the spacing of float32 is 2^-8 and
+        # neighbouring rows' keys collide)
+        perm1 = torch.argsort(torch.rand(cand.shape[0], generator=g, device=off.device))
+        perm = perm1[torch.sort(row[perm1], stable=True)[1]]
         rank = torch.arange(cand.shape[0], device=off.device) - off[:-1][row]
         keep = rank < cap
         cand = cand[perm][keep]

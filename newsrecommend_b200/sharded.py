@@ -17,9 +17,9 @@ import torch.distributed as dist
 
 
 def shard_range(nb: int, world: int, rank: int) -> tuple[int, int]:
-    per = (nb + world - 1) // world
-    lo = min(nb, rank * per)
-    return lo, min(nb, lo + per)
+    """Balanced contiguous row ranges: shard sizes differ by at most one row and no shard is empty
+    while nb >= world (ceil-sized ranges leave trailing shards empty, e.g. nb = 9, world = 8)."""
+    return nb * rank // world, nb * (rank + 1) // world
 
 
 def _gpu_merge(Dp: torch.Tensor, Ip: torch.Tensor, metric: int):

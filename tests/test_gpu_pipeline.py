@@ -107,3 +107,28 @@ def test_finalize_and_hit_rate_match_the_scripts(tmp_path):
     assert (np.diff(coff) <= 11).all()
     for u in range(nu):
         assert set(ccand[coff[u]:coff[u + 1]].tolist()) <= set(cand[off[u]:off[u + 1]].tolist()) | {int(gt[u])}
+
+
+def test_finalize_cap_keeps_candidates_in_their_own_row_at_scale():
+    """with >= 1e5 users the cap's shuffle must not move candidates across user rows
+    (a float32 `rand + row` key collides between neighbouring rows beyond row ~2^16)."""
+    from newsrecommend_b200 import pipeline
+    rng = np.random.default_rng(1)
+    nu = 120_000
+    lens = rng.integers(20, 60, size=nu)
+    off = np.zeros(nu + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    # candidate value encodes its row: every kept candidate must decode to its own row
+    row = np.repeat(np.arange(nu, dtype=np.int64), lens)
+    cand = row * 100 + (np.arange(off[-1]) - off[row])
+    gt = np.arange(nu, dtype=np.int64) * 100 + 99  # never present: appended to every row
+    coff, ccand = pipeline.finalize_candidates(off, cand, gt, cap=30, seed=3)
+    coff, ccand = coff.cpu().numpy(), ccand.cpu().numpy()
+    assert np.array_equal(np.diff(coff), np.minimum(lens, 30) + 1)
+    crow = np.repeat(np.arange(nu, dtype=np.int64), np.diff(coff))
+    assert np.array_equal(ccand // 100, crow), "a candidate moved to another user's list"
+    assert np.array_equal(ccand[coff[1:] - 1], gt)
+    # sampled without replacement, and not just a prefix (the sample is random)
+    assert np.unique(ccand).size == ccand.size
+    tail = ccand[coff[nu - 1000]:] % 100
+    assert np.unique(tail[tail != 99]).size > 40  # the last rows still draw from their whole lists
