@@ -187,6 +187,15 @@ int nrb_csr_contains(const int64_t* off, const int64_t* ids, const int64_t* targ
 int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts, int64_t nq, int32_t k,
                    int32_t metric, float* D, int64_t* I, void* stream);
 
+/* Wire format of the all-to-all by query range (the exchange step of the catalog-sharded search):
+ * P[i] = (fp32 bits of D[i]) << 32 | uint32(I[i] - id_base), 0xffffffff in the low word when
+ * I[i] < 0. 8 bytes per candidate, one collective instead of two. n = nq * k elements. */
+int nrb_pack_topk(const float* D, const int64_t* I, int64_t id_base, int64_t n, uint64_t* P, void* stream);
+/* P u64[nparts, nq, k] (each part best-first) + bases i64[nparts] (device; the id_base each part was
+ * packed with) -> global top-k D f32[nq, k], I i64[nq, k]. Exact ties resolve by part order. */
+int nrb_merge_topk_packed(const uint64_t* P, const int64_t* bases, int32_t nparts, int64_t nq, int32_t k,
+                          int32_t metric, float* D, int64_t* I, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ SYMBOLS = [
     "nrb_ivf_build_lists_workspace", "nrb_ivf_build_lists",
     "nrb_ivf_search_workspace", "nrb_ivf_search",
     "nrb_merge_topk", "nrb_expand_lists", "nrb_csr_contains",
+    "nrb_pack_topk", "nrb_merge_topk_packed",
 ]
 
 
@@ -79,6 +80,8 @@ lib.nrb_ivf_search_workspace.argtypes = [_i64, _i32, _i32, _i32, _i32, _i32]
 lib.nrb_ivf_search.argtypes = [_mp, _mp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz,
                                _i32, _vp]
 lib.nrb_merge_topk.argtypes = [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]
+lib.nrb_pack_topk.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp]
+lib.nrb_merge_topk_packed.argtypes = [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]
 lib.nrb_expand_lists.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _vp]
 lib.nrb_csr_contains.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
 
