@@ -134,17 +134,46 @@ int nrb_plan_flat_describe(int64_t nq, int64_t nb, int32_t k, int32_t path, int3
 /* ---- K1b: k-means centroid update (Clustering.cpp compute_centroids) ---------------------- */
 /* Replaces the update step of clustering.train (Retrieval.py:18). x_raw is the packed raw
  * plane [n, kp]; assign i64[n] in [0, k). Writes centroids f32[k, d] (row stride d) as the
- * mean of the assigned rows (fp64 accumulation in point order, rounded to fp32, times
- * 1.0f/count like faiss) and hassign f32[k] = counts. Empty clusters keep zeros. */
-size_t nrb_kmeans_update_workspace(int64_t n, int32_t k);
+ * mean of the assigned rows and hassign f32[k] = counts. Empty clusters keep zeros.
+ * A segmented reduction over the counting-sorted rows, balanced under list skew: every list is
+ * cut into 64-row chunks, one block per chunk sums in fp64 (fixed association), one block per
+ * centroid adds the chunk partials in order, rounds to fp32 and multiplies by 1.0f/count like
+ * faiss. Deterministic. HBM-bound: reads n * kp * 4 bytes. */
+size_t nrb_kmeans_update_workspace(int64_t n, int32_t k, int32_t kp);
 int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32_t kp,
                       const int64_t* assign, int32_t k, float* centroids, float* hassign,
                       void* workspace, size_t workspace_bytes, void* stream);
 /* Host-side pieces of Clustering::train that faiss also runs on the host (tiny, sequential,
  * RNG-driven): rand_perm (utils/random.cpp, std::mt19937, seed 1234 subsample / seed+1 init)
- * and split_clusters (EPS = 1/1024, rng(1234)). Return value of split = nsplit. */
+ * and split_clusters (EPS = 1/1024, rng(1234)). Return value of split = nsplit. These two
+ * restate third-party faiss routines (facebookresearch/faiss, MIT licence: utils/random.cpp
+ * rand_perm, Clustering.cpp split_clusters) because RNG-exact k-means needs their exact
+ * arithmetic; they are not taken from /root/reference, which holds no native code. */
 int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed);
 int nrb_split_clusters_host(int32_t d, int32_t k, int64_t n, float* hassign, float* centroids);
+/* split_clusters on the DEVICE (one block; std::mt19937(1234) restated in the kernel), so that
+ * the training loop needs no host round trip: hassign f32[k] and centroids f32[k, d] are
+ * updated in place; stats3 f64[3]: [1] = imbalance factor k * sum(size^2) / n^2 of the sizes
+ * on entry, [2] = number of splits (-1: no cluster could be split); [0] is not touched. */
+int nrb_split_clusters(int32_t d, int32_t k, int64_t n, float* hassign, float* centroids, double* stats3,
+                       void* stream);
+/* Clustering::train's iteration loop (Retrieval.py:18; IndexIVFFlat.train) as ONE call: niter x
+ * { pack the centroids, exact nearest-centroid assignment of every row (K2 with k = 1: fp16 filter +
+ * exact fp32 refine when x carries h16 + row scales and kp <= 256, else the 1xTF32 filter on hi,
+ * else 3xTF32 on hi / lo; rows a filter flags are recomputed exactly by a device-driven kernel),
+ * K1b update + objective (sum over rows of |x - c|^2 or x.c against the centroids the iteration
+ * started with, exact fp32 products, fixed-order fp64 sums), device split_clusters, optional L2
+ * renormalisation (spherical) }, all queued on `stream` with NO host synchronisation.
+ * x: packed training rows (raw, norms, and h16 + h16_row_scale or hi [+ lo]); x->max_norm must
+ * hold the largest row norm (it bounds every centroid: a mean is no longer than the longest row,
+ * a split scales by at most 1 + 1/1024). centroids f32[k, d]: initial centroids in (rows of x, or
+ * anything no longer than x->max_norm), final centroids out. assign i64[n] (optional): the last
+ * iteration's assignment. stats f64[niter, 4] (device): objective, imbalance factor, nsplit, 0.
+ * `metric` is the assigner's metric (NRB_METRIC_L2 for IndexFlatL2 / the reference's quantizer). */
+size_t nrb_kmeans_train_workspace(int64_t n, int32_t k, int32_t kp);
+int nrb_kmeans_train(const nrb_matrix* x, int32_t k, int32_t niter, int32_t metric, int32_t spherical,
+                     float* centroids, int64_t* assign, double* stats, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* ---- K3: IVF lists (ArrayInvertedLists + search_preassigned / IVFFlatScanner) ------------- */
 /* Stable counting sort of rows by list id. Replaces the 300 boolean masks at Retrieval.py:23
@@ -186,6 +215,39 @@ int nrb_csr_contains(const int64_t* off, const int64_t* ids, const int64_t* targ
  * Sits after the NCCL all-gather of the catalog-sharded search (north_star item 4). */
 int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts, int64_t nq, int32_t k,
                    int32_t metric, float* D, int64_t* I, void* stream);
+
+/* ---- low-latency path for tiny batches (csrc/small_batch.cu)
+ * faiss's own route for nq < distance_compute_blas_threshold (20): no GEMM, every (query, item)
+ * distance computed directly in fp32 (L2 as sum (q - x)^2, not via norms) and selected exactly
+ * (knn_inner_product / knn_L2sqr sequential branch). This is the route each of the
+ * 50,000 `centroid_index.search(profile, 1)` calls of Retrieval.py:30-32 takes. Here: every item
+ * row is read once with 128-bit loads (a warp per row, several rows in flight, HBM-bound), the
+ * scores of one query go to a scratch row and the top-k is selected exactly by radix select (in two
+ * levels of 8,192-element slices for long rows); catalogs of up to
+ * 8,192 rows (the centroid index) run as ONE launch with the scores in shared memory. No plan
+ * kernels, no packing of the queries (xq is plain fp32 [nq, d], row stride ldq), no host
+ * synchronisation. nq <= NRB_SMALL_MAX_NQ, k <= NRB_MAX_K; b needs only its raw plane. */
+#define NRB_SMALL_MAX_NQ 64
+size_t nrb_search_small_workspace(int64_t nq, int64_t nb, int32_t k);
+int nrb_search_small(const float* xq, int64_t ldq, int32_t nq, int32_t d, const nrb_matrix* b, int32_t metric,
+                     int32_t k, int64_t id_base, float* D, int64_t* I, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* The same with HOST query rows in and HOST results out (numpy in, numpy out; Retrieval.py:31-32):
+ * the library keeps a page-locked staging buffer that is MAPPED into the device address space
+ * (grow-only, per device): the kernels read the query rows from it and write D / I into it, so a
+ * call is the kernel launch(es) plus one stream synchronisation, no copy calls. Synchronous. */
+int nrb_search_small_host(const nrb_matrix* b, const float* xq_host, int32_t nq, int32_t d, int32_t metric, int32_t k,
+                          int64_t id_base, float* D_host, int64_t* I_host, void* stream);
+/* HBM-regime inverted-list scan for small batches (north_star item 3; IVFFlatScanner over
+ * nprobe lists per query, Retrieval.py:32-34 in IndexIVFFlat form): block per (query, probed
+ * list, 256-row chunk), a warp per row with 128-bit loads of the list-contiguous raw plane,
+ * exact fp32 scores to scratch, block-per-query radix select. Algorithmic bytes = sum over
+ * (query, probed list) of |list| * kp * 4. nq * nprobe <= 65,535. xq plain fp32 [nq, d]. */
+size_t nrb_ivf_scan_small_workspace(int64_t nq, int32_t nprobe, int32_t max_list_len, int64_t ntotal, int32_t k);
+int nrb_ivf_scan_small(const float* xq, int64_t ldq, int32_t nq, int32_t d, const nrb_matrix* lists,
+                       const int32_t* offsets, int32_t nlist, int32_t max_list_len, const int64_t* ids,
+                       const int64_t* coarse, int32_t nprobe, int32_t metric, int32_t k, float* D, int64_t* I,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Wire format of the all-to-all by query range (the exchange step of the catalog-sharded search):
  * P[i] = (fp32 bits of D[i]) << 32 | uint32(I[i] - id_base), 0xffffffff in the low word when

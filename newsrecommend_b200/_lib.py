@@ -17,6 +17,7 @@ METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC1, PATH_TC16 = 0, 1, 2, 3, 4
 MAX_K = 128
+SMALL_MAX_NQ = 64  # NRB_SMALL_MAX_NQ
 
 # every symbol include/nrb200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -25,11 +26,14 @@ SYMBOLS = [
     "nrb_pack_rows", "nrb_pack_rows_h16", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
     "nrb_search_flat_workspace", "nrb_search_flat", "nrb_fallback_query_count", "nrb_plan_flat_describe",
     "nrb_kmeans_update_workspace", "nrb_kmeans_update",
-    "nrb_rand_perm_host", "nrb_split_clusters_host",
+    "nrb_rand_perm_host", "nrb_split_clusters_host", "nrb_split_clusters",
+    "nrb_kmeans_train_workspace", "nrb_kmeans_train",
     "nrb_ivf_build_lists_workspace", "nrb_ivf_build_lists",
     "nrb_ivf_search_workspace", "nrb_ivf_search",
     "nrb_merge_topk", "nrb_expand_lists", "nrb_csr_contains",
     "nrb_pack_topk", "nrb_merge_topk_packed",
+    "nrb_search_small_workspace", "nrb_search_small", "nrb_search_small_host",
+    "nrb_ivf_scan_small_workspace", "nrb_ivf_scan_small",
 ]
 
 
@@ -68,10 +72,14 @@ lib.nrb_search_flat.argtypes = [_mp, _mp, _i32, _i32, _i64, _vp, _vp, _vp, _sz, 
 lib.nrb_fallback_query_count.restype = _i64
 lib.nrb_plan_flat_describe.argtypes = [_i64, _i64, _i32, _i32, _vp]
 lib.nrb_kmeans_update_workspace.restype = _sz
-lib.nrb_kmeans_update_workspace.argtypes = [_i64, _i32]
+lib.nrb_kmeans_update_workspace.argtypes = [_i64, _i32, _i32]
 lib.nrb_kmeans_update.argtypes = [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]
 lib.nrb_rand_perm_host.argtypes = [_vp, _i64, _i64]
 lib.nrb_split_clusters_host.argtypes = [_i32, _i32, _i64, _vp, _vp]
+lib.nrb_split_clusters.argtypes = [_i32, _i32, _i64, _vp, _vp, _vp, _vp]
+lib.nrb_kmeans_train_workspace.restype = _sz
+lib.nrb_kmeans_train_workspace.argtypes = [_i64, _i32, _i32]
+lib.nrb_kmeans_train.argtypes = [_mp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]
 lib.nrb_ivf_build_lists_workspace.restype = _sz
 lib.nrb_ivf_build_lists_workspace.argtypes = [_i64, _i32]
 lib.nrb_ivf_build_lists.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]
@@ -82,6 +90,14 @@ lib.nrb_ivf_search.argtypes = [_mp, _mp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, 
 lib.nrb_merge_topk.argtypes = [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]
 lib.nrb_pack_topk.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp]
 lib.nrb_merge_topk_packed.argtypes = [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]
+lib.nrb_search_small_workspace.restype = _sz
+lib.nrb_search_small_workspace.argtypes = [_i64, _i64, _i32]
+lib.nrb_search_small.argtypes = [_vp, _i64, _i32, _i32, _mp, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _vp]
+lib.nrb_search_small_host.argtypes = [_mp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp]
+lib.nrb_ivf_scan_small_workspace.restype = _sz
+lib.nrb_ivf_scan_small_workspace.argtypes = [_i64, _i32, _i32, _i64, _i32]
+lib.nrb_ivf_scan_small.argtypes = [_vp, _i64, _i32, _i32, _mp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp,
+                                   _vp, _sz, _vp]
 lib.nrb_expand_lists.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _vp]
 lib.nrb_csr_contains.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
 

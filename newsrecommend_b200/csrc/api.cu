@@ -8,6 +8,8 @@
 #include <random>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -603,6 +605,11 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     if ((rc = launch_gather_refine(w.part_key, w.part_idx, w.part_cnt, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
                                    id_base, nullptr, w.flags, D, I, st))) return rc;
     if ((rc = launch_compact_flags(w.flags, q->n, w.flag_list, w.flag_count, st))) return rc;
+    if (k == 1 && b->n <= K1_FALLBACK_MAX_ROWS) {
+        // nearest-centroid assignment (k-means, IndexIVFFlat.add): flagged rows are recomputed exactly by
+        // a kernel driven by the device-side list -- no host round trip, the call stays asynchronous
+        return launch_exact_k1_fallback(q, b, metric, id_base, w.flag_list, w.flag_count, D, I, st);
+    }
     int nflag = 0;
     NRB_CUDA_CHECK(cudaMemcpyAsync(&nflag, w.flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     NRB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -870,6 +877,104 @@ extern "C" int nrb_ivf_search(const nrb_matrix* q, const nrb_matrix* lists, cons
     if (path == NRB_PATH_AUTO) path = filt_ok ? NRB_PATH_TC16 : NRB_PATH_TC;
     return ivf_search_impl(q, lists, offsets, nlist, max_list_len, ids, coarse, nprobe, metric, k, D, I, workspace,
                            workspace_bytes, path, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------ fused k-means
+namespace nrb {
+struct KmTrainWs {
+    float *craw, *chi, *clo, *cnorms, *hassign, *dis, *cent_in;
+    __half* ch16;
+    int64_t* assign;
+    void* upd;
+    size_t upd_bytes;
+    void* search;
+    size_t search_bytes;
+    size_t total;
+};
+static KmTrainWs carve_km_train(void* ws, int64_t n, int k, int d, int kp) {
+    Carver c(ws);
+    KmTrainWs w;
+    w.craw = c.take<float>((size_t)k * kp);
+    w.chi = c.take<float>((size_t)k * kp);
+    w.clo = c.take<float>((size_t)k * kp);
+    w.ch16 = c.take<__half>((size_t)k * kp);
+    w.cnorms = c.take<float>(k);
+    w.hassign = c.take<float>(k);
+    w.cent_in = c.take<float>((size_t)k * d);
+    w.dis = c.take<float>(n);
+    w.assign = c.take<int64_t>(n);
+    w.upd_bytes = kmeans_update_ws(n, k, kp);
+    w.upd = c.take<char>(w.upd_bytes);
+    w.search_bytes = nrb_search_flat_workspace(n, k, 1, kp);
+    w.search = c.take<char>(w.search_bytes);
+    w.total = c.off;
+    return w;
+}
+}  // namespace nrb
+
+extern "C" size_t nrb_kmeans_train_workspace(int64_t n, int32_t k, int32_t kp) {
+    if (n <= 0 || k <= 0 || kp <= 0) return 256;
+    return carve_km_train(nullptr, n, k, kp, kp).total + 256;
+}
+
+extern "C" int nrb_kmeans_train(const nrb_matrix* x, int32_t k, int32_t niter, int32_t metric, int32_t spherical,
+                                float* centroids, int64_t* assign, double* stats, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    NRB_REQUIRE(x && centroids && stats && workspace, "kmeans_train: null argument");
+    NRB_REQUIRE(x->raw && x->norms, "kmeans_train: the training rows need their raw plane and norms");
+    NRB_REQUIRE(metric == NRB_METRIC_INNER_PRODUCT || metric == NRB_METRIC_L2, "kmeans_train: bad metric %d", metric);
+    NRB_REQUIRE(k > 0 && niter >= 0 && x->n > k && x->n < (1LL << 31) && x->kp % 32 == 0 && x->kp <= 2048,
+                "kmeans_train: bad sizes n=%lld k=%d", (long long)x->n, k);
+    int rc = require_device();
+    if (rc) return rc;
+    const int64_t n = x->n;
+    const int d = x->d, kp = x->kp;
+    const KmTrainWs w = carve_km_train(workspace, n, k, d, kp);
+    if (workspace_bytes < w.total) {
+        set_error("kmeans_train: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return NRB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // Norm bound of every centroid this loop can produce, known on the host: a mean of rows is no longer
+    // than the longest row, and split_clusters scales coordinates by at most (1 + 1/1024) per split
+    // (<= k splits per iteration); spherical centroids have norm 1. It sizes the filter's error margin
+    // and the fp16 scale of the centroid plane, so the loop never reads a norm back.
+    float bound = x->max_norm * powf(1.f + 1.f / 1024.f, (float)(k < 1024 ? k : 1024)) * 1.0001f;
+    if (spherical && bound < 1.0001f) bound = 1.0001f;
+    // assignment path: fp16 filter + exact refine when the rows carry their scaled fp16 plane, else the
+    // 1xTF32 filter (hi plane), else 3xTF32; k = 1 makes every one of them free of host round trips
+    const bool f16 = x->h16 && x->h16_row_scale && x->max_norm > 0.f && kp <= 256;
+    const bool f32 = !f16 && x->hi && x->max_norm > 0.f && kp <= 256;
+    NRB_REQUIRE(f16 || f32 || (x->hi && x->lo), "kmeans_train: the training rows need h16 (+ row scales), or hi, or hi + lo planes");
+    const int path = f16 ? NRB_PATH_TC16 : f32 ? NRB_PATH_TC1 : NRB_PATH_TC;
+    nrb_matrix cm;
+    memset(&cm, 0, sizeof(cm));
+    cm.raw = w.craw;
+    cm.hi = w.chi;
+    cm.lo = w.clo;
+    cm.norms = w.cnorms;
+    cm.n = k;
+    cm.d = d;
+    cm.kp = kp;
+    cm.max_norm = bound;
+    if (f16) {
+        cm.h16 = w.ch16;
+        cm.h16_scale = ldexpf(1.f, 14 - ilogbf(bound));
+    }
+    for (int it = 0; it < niter; it++) {
+        double* s = stats + (size_t)it * 4;
+        if ((rc = launch_pack_rows(centroids, k, d, d, kp, w.craw, w.chi, w.clo, w.cnorms, st))) return rc;
+        if (f16 && (rc = nrb_pack_rows_h16(w.craw, k, d, kp, kp, cm.h16_scale, w.ch16, nullptr, stream))) return rc;
+        if ((rc = search_flat_impl(x, &cm, metric, 1, 0, w.dis, w.assign, w.search, w.search_bytes, path, st))) return rc;
+        NRB_CUDA_CHECK(cudaMemcpyAsync(w.cent_in, centroids, (size_t)k * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if ((rc = launch_kmeans_update(x->raw, n, d, kp, w.assign, k, centroids, w.hassign, w.upd, w.cent_in, metric, s, st)))
+            return rc;
+        if ((rc = launch_km_split(d, k, n, w.hassign, centroids, s, st))) return rc;
+        if (spherical && (rc = nrb_normalize_l2(centroids, k, d, d, stream))) return rc;
+    }
+    if (assign && niter > 0)
+        NRB_CUDA_CHECK(cudaMemcpyAsync(assign, w.assign, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return NRB_OK;
 }
 
 extern "C" int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed) {

@@ -88,6 +88,19 @@ int launch_gather_rows(const float* src, int width, const int32_t* idx, int div,
 int launch_gather_scalar(const float* src, const int32_t* idx, int div, int64_t n, float* dst,
                          cudaStream_t st);
 
+size_t kmeans_update_ws(int64_t n, int k, int kp);
+// cent_in (optional, f32[k, d]): the centroids the assignment was made against -> obj_out (f64) = the
+// k-means objective sum over rows of |x - c|^2 (L2) or x.c (IP), exact fp32 products, fixed-order fp64 sum
+int launch_kmeans_update(const float* x_raw, int64_t n, int d, int kp, const int64_t* assign, int k, float* centroids,
+                         float* hassign, void* workspace, const float* cent_in, int metric, double* obj_out,
+                         cudaStream_t st);
+int launch_km_split(int d, int k, int64_t n, float* hassign, float* centroids, double* stats, cudaStream_t st);
+
+// small_batch.cu: exact fp32 recompute of the rows listed in list[0 .. *count) for k = 1 (device-driven)
+constexpr int K1_FALLBACK_MAX_ROWS = 65536;  // item rows up to which flagged k = 1 rows are recomputed on the device
+int launch_exact_k1_fallback(const nrb_matrix* q, const nrb_matrix* b, int metric, int64_t id_base, const int* list,
+                             const int* count, float* D, int64_t* I, cudaStream_t st);
+
 int sm_count();
 
 }  // namespace nrb

@@ -225,46 +225,257 @@ __global__ void cs_scatter_kernel(const KeyT* __restrict__ key, int64_t n, int n
 }
 
 // ------------------------------------------------------------------- K1b centroid update
-// Block per centroid. Threads = (kp/4 float4 columns) x RS row slices; each thread sums its
-// slice's rows in source order in fp64; slices are combined in a fixed order, so the result is
-// deterministic. mean = float(sum) * (1.0f / count)  (Clustering.cpp compute_centroids).
-template <int RS>
-__global__ void kmeans_update_kernel(const float* __restrict__ x_raw, int kp, int d,
-                                     const int* __restrict__ offsets,
-                                     const int* __restrict__ order, float* __restrict__ centroids,
-                                     float* __restrict__ hassign) {
-    extern __shared__ double part[];  // [RS][kp]
-    const int c = blockIdx.x;
-    const int w4 = kp >> 2;
-    const int col4 = threadIdx.x % w4;
-    const int slice = threadIdx.x / w4;
-    const int r0 = offsets[c], r1 = offsets[c + 1];
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    if (slice < RS) {
-        for (int r = r0 + slice; r < r1; r += RS) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(x_raw + (int64_t)order[r] * kp) + col4);
-            a0 += v.x;
-            a1 += v.y;
-            a2 += v.z;
-            a3 += v.w;
-        }
-        double* p = part + (int64_t)slice * kp + col4 * 4;
-        p[0] = a0;
-        p[1] = a1;
-        p[2] = a2;
-        p[3] = a3;
-    }
+// Segmented reduction over the counting-sorted row order, balanced under list skew: every
+// centroid's run of rows is cut into chunks of KM_CHUNK rows (a chunk never crosses a centroid
+// boundary), one block per chunk sums its rows in fp64 (threads = kp/4 float4 columns x `slices`
+// row slices, each slice in source order, slices combined in a fixed order), and one block per
+// centroid adds the chunk partials in chunk order. Every sum has a fixed association, so the
+// result is deterministic and independent of the grid; a 18,000-row list is 280 blocks of work
+// instead of one. mean = float(sum) * (1.0f / count)  (Clustering.cpp compute_centroids).
+constexpr int KM_CHUNK = 64;
+
+// chunk_base[c] = number of chunks of centroids < c (exclusive scan of ceil(len / KM_CHUNK));
+// chunk_base[k] = total. One block.
+__global__ void km_plan_kernel(const int* __restrict__ offsets, int k, int* __restrict__ chunk_base) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const int cnt = r1 - r0;
-    if (threadIdx.x == 0) hassign[c] = (float)cnt;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) {
-        double s = 0;
+    for (int base = 0; base < k; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const int v = c < k ? (offsets[c + 1] - offsets[c] + KM_CHUNK - 1) / KM_CHUNK : 0;
+        int inc = v;
 #pragma unroll
-        for (int q = 0; q < RS; q++) s += part[(int64_t)q * kp + j];
-        float m = 0.f;
-        if (cnt > 0) m = (float)s * (1.0f / (float)cnt);
-        centroids[(int64_t)c * d + j] = m;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int before = carry;
+        for (int w = 0; w < warp; w++) before += wsum[w];
+        if (c < k) chunk_base[c] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < nw; w++) t += wsum[w];
+            carry += t;
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) chunk_base[k] = carry;
+}
+
+__global__ void km_partial_kernel(const float* __restrict__ x_raw, int kp, const int* __restrict__ offsets,
+                                  const int* __restrict__ order, const int* __restrict__ chunk_base, int k, int slices,
+                                  double* __restrict__ partial, const float* __restrict__ cent_in, int d, int l2,
+                                  double* __restrict__ obj_part) {
+    extern __shared__ double part[];  // [slices][kp]
+    const int j = blockIdx.x;
+    if (j >= chunk_base[k]) return;
+    int lo = 0, hi = k;  // largest c with chunk_base[c] <= j (an empty centroid shares its base with the next one)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_base[mid] <= j) lo = mid; else hi = mid;
+    }
+    const int c = lo;
+    const int r0 = offsets[c] + (j - chunk_base[c]) * KM_CHUNK;
+    const int r1 = min(offsets[c + 1], r0 + KM_CHUNK);
+    const int w4 = kp >> 2;
+    const int col4 = threadIdx.x % w4, slice = threadIdx.x / w4;
+    // objective against the centroid the rows were assigned to (the one the iteration started with)
+    float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cent_in) {
+        const float* cr = cent_in + (int64_t)c * d;
+        const int c0 = col4 * 4;
+        cc.x = c0 < d ? cr[c0] : 0.f;
+        cc.y = c0 + 1 < d ? cr[c0 + 1] : 0.f;
+        cc.z = c0 + 2 < d ? cr[c0 + 2] : 0.f;
+        cc.w = c0 + 3 < d ? cr[c0 + 3] : 0.f;
+    }
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, ob = 0;
+#pragma unroll 4
+    for (int r = r0 + slice; r < r1; r += slices) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x_raw + (int64_t)order[r] * kp) + col4);
+        a0 += v.x;
+        a1 += v.y;
+        a2 += v.z;
+        a3 += v.w;
+        float t;
+        if (l2) {
+            const float e0 = v.x - cc.x, e1 = v.y - cc.y, e2 = v.z - cc.z, e3 = v.w - cc.w;
+            t = fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
+        } else {
+            t = fmaf(v.w, cc.w, fmaf(v.z, cc.z, fmaf(v.y, cc.y, v.x * cc.x)));
+        }
+        ob += t;
+    }
+    double* p = part + (int64_t)slice * kp + col4 * 4;
+    p[0] = a0;
+    p[1] = a1;
+    p[2] = a2;
+    p[3] = a3;
+    __syncthreads();
+    for (int col = threadIdx.x; col < kp; col += blockDim.x) {
+        double s = 0;
+        for (int q = 0; q < slices; q++) s += part[(int64_t)q * kp + col];
+        partial[(int64_t)j * kp + col] = s;
+    }
+    if (obj_part) {  // fixed-order block sum (blockDim <= 1024 = slices * kp / 4 <= the part[] capacity in doubles)
+        __syncthreads();
+        part[threadIdx.x] = ob;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0;
+            for (int t = 0; t < (int)blockDim.x; t++) s += part[t];
+            obj_part[j] = s;
+        }
+    }
+}
+
+__global__ void km_finish_kernel(const double* __restrict__ partial, const int* __restrict__ chunk_base,
+                                 const int* __restrict__ offsets, int kp, int d, int k, float* __restrict__ centroids,
+                                 float* __restrict__ hassign, const double* __restrict__ obj_part,
+                                 double* __restrict__ obj_out) {
+    const int c = blockIdx.x;
+    const int j0 = chunk_base[c], j1 = chunk_base[c + 1];
+    const int cnt = offsets[c + 1] - offsets[c];
+    if (threadIdx.x == 0) hassign[c] = (float)cnt;
+    for (int col = threadIdx.x; col < d; col += blockDim.x) {
+        double s = 0;
+#pragma unroll 8
+        for (int j = j0; j < j1; j++) s += partial[(int64_t)j * kp + col];
+        centroids[(int64_t)c * d + col] = cnt > 0 ? (float)s * (1.0f / (float)cnt) : 0.f;
+    }
+    if (obj_out && c == 0) {  // objective = sum of the chunk objectives, fixed order
+        __shared__ double red[256];
+        const int total = chunk_base[k];
+        double s = 0;
+        for (int j = threadIdx.x; j < total; j += blockDim.x) s += obj_part[j];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *obj_out = red[0];
+    }
+}
+
+// faiss Clustering.cpp split_clusters on the device (same arithmetic as nrb_split_clusters_host
+// in api.cu, which the tests compare it with): for every empty cluster ci, walk the clusters
+// round-robin and pick cj with probability (size_cj - 1) / (n - k) using std::mt19937(1234)
+// (restated below: MT19937 of Matsumoto & Nishimura with the standard tempering), copy cj's centroid
+// to ci and perturb the pair symmetrically by +-1/1024, split the size. Thread 0 draws the
+// (ci, cj) pairs in batches; the block applies each batch in order. stats[1] = imbalance factor
+// k * sum(size^2) / n^2 of the assignment BEFORE the split, stats[2] = number of splits (-1 if no
+// cluster could be split).
+struct Mt19937Dev {
+    uint32_t* s;  // 624 words of shared memory
+    int idx;
+    __device__ void seed(uint32_t v) {
+        s[0] = v;
+        for (int i = 1; i < 624; i++) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    __device__ uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; i++) {
+                const uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+                s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = s[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+};
+
+constexpr int KM_SPLIT_BATCH = 512;
+
+__global__ void km_split_kernel(int d, int k, int64_t n, float* __restrict__ hassign, float* __restrict__ centroids,
+                                double* __restrict__ stats) {
+    __shared__ uint32_t mt_state[624];
+    __shared__ int pair_ci[KM_SPLIT_BATCH], pair_cj[KM_SPLIT_BATCH];
+    __shared__ int npairs, next_ci, any_empty, failed;
+    __shared__ double red[1024];
+    // imbalance factor + "is any cluster empty"
+    double s2 = 0;
+    int empty = 0;
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+        const double h = hassign[c];
+        s2 += h * h;
+        empty |= (h == 0.0) ? 1 : 0;
+    }
+    red[threadIdx.x] = s2;
+    if (threadIdx.x == 0) { any_empty = 0; next_ci = 0; failed = 0; }
+    __syncthreads();
+    if (empty) any_empty = 1;
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[1] = red[0] * (double)k / ((double)n * (double)n);
+        stats[2] = 0.0;
+    }
+    if (!any_empty) return;
+    Mt19937Dev mt{mt_state, 624};
+    if (threadIdx.x == 0) mt.seed(1234u);
+    const double EPS = 1 / 1024.;
+    int nsplit = 0;
+    int cj = 0;  // (thread 0) faiss restarts cj at 0 for every empty cluster
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int np = 0;
+            int ci = next_ci;
+            for (; ci < k && np < KM_SPLIT_BATCH; ci++) {
+                if (hassign[ci] != 0) continue;
+                long long guard = 0;
+                for (cj = 0;; cj = (cj + 1) % k) {
+                    const float p = (float)(((double)hassign[cj] - 1.0) / (double)(float)(n - k));
+                    const float r = (float)mt.next() / 4294967296.0f;
+                    if (r < p) break;
+                    if (++guard > 100000000LL) { failed = 1; break; }
+                }
+                if (failed) break;
+                pair_ci[np] = ci;
+                pair_cj[np] = cj;
+                np++;
+                hassign[ci] = hassign[cj] / 2;
+                hassign[cj] -= hassign[ci];
+            }
+            next_ci = ci;
+            npairs = np;
+        }
+        __syncthreads();
+        const int np = npairs;
+        for (int e = 0; e < np; e++) {
+            float* a = centroids + (size_t)pair_ci[e] * d;
+            float* b = centroids + (size_t)pair_cj[e] * d;
+            for (int j = threadIdx.x; j < d; j += blockDim.x) {
+                const float v = b[j];
+                if (j % 2 == 0) {
+                    a[j] = (float)((double)v * (1 + EPS));
+                    b[j] = (float)((double)v * (1 - EPS));
+                } else {
+                    a[j] = (float)((double)v * (1 - EPS));
+                    b[j] = (float)((double)v * (1 + EPS));
+                }
+            }
+            __syncthreads();
+        }
+        nsplit += np;
+        const bool done = next_ci >= k || failed;
+        __syncthreads();
+        if (done) break;
+    }
+    if (threadIdx.x == 0) stats[2] = failed ? -1.0 : (double)nsplit;
 }
 
 // ------------------------------------------------------------------- select / merge (K4)
@@ -963,9 +1174,71 @@ extern "C" int nrb_ivf_build_lists(const int64_t* assign, int64_t n, int32_t nli
                                     workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" size_t nrb_kmeans_update_workspace(int64_t n, int32_t k) {
-    return counting_sort_ws(n, k) + align_up((size_t)(k + 2) * sizeof(int), 256) +
-           align_up((size_t)(n > 0 ? n : 1) * sizeof(int), 256);
+namespace nrb {
+
+struct KmUpdateWs {
+    void* cs;
+    size_t cs_bytes;
+    int *offsets, *order, *chunk_base;
+    double *partial, *obj_part;
+    size_t total;
+};
+
+static KmUpdateWs carve_km_update(void* ws, int64_t n, int k, int kp) {
+    char* w = (char*)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = w ? w + off : nullptr; off += align_up(bytes, 256); return r; };
+    KmUpdateWs u;
+    u.cs_bytes = counting_sort_ws(n, k);
+    u.cs = take(u.cs_bytes);
+    u.offsets = (int*)take((size_t)(k + 2) * sizeof(int));
+    u.order = (int*)take((size_t)(n > 0 ? n : 1) * sizeof(int));
+    u.chunk_base = (int*)take((size_t)(k + 2) * sizeof(int));
+    u.partial = (double*)take((size_t)(n / KM_CHUNK + k + 1) * kp * sizeof(double));
+    u.obj_part = (double*)take((size_t)(n / KM_CHUNK + k + 1) * sizeof(double));
+    u.total = off;
+    return u;
+}
+
+size_t kmeans_update_ws(int64_t n, int k, int kp) { return carve_km_update(nullptr, n, k, kp).total; }
+
+// centroids f32[k, d], hassign f32[k] from assign i64[n] (K1b): counting sort + plan + partial + finish
+int launch_kmeans_update(const float* x_raw, int64_t n, int d, int kp, const int64_t* assign, int k, float* centroids,
+                         float* hassign, void* workspace, const float* cent_in, int metric, double* obj_out,
+                         cudaStream_t st) {
+    const KmUpdateWs u = carve_km_update(workspace, n, k, kp);
+    int rc = launch_counting_sort_i64(assign, n, k, u.offsets, u.order, nullptr, u.cs, u.cs_bytes, st);
+    if (rc) return rc;
+    km_plan_kernel<<<1, 1024, 0, st>>>(u.offsets, k, u.chunk_base);
+    NRB_LAUNCH_CHECK();
+    const int w4 = kp / 4;
+    int slices = 256 / w4;
+    slices = slices < 1 ? 1 : (slices > 8 ? 8 : slices);
+    const int threads = w4 * slices;
+    NRB_REQUIRE(threads <= 1024, "kmeans_update: kp %d too large", kp);
+    const size_t smem = (size_t)slices * kp * sizeof(double);
+    const unsigned nchunks = (unsigned)(n / KM_CHUNK + k + 1);
+    const bool obj = cent_in && obj_out;
+    km_partial_kernel<<<nchunks, threads, smem, st>>>(x_raw, kp, u.offsets, u.order, u.chunk_base, k, slices, u.partial,
+                                                      obj ? cent_in : nullptr, d, metric == NRB_METRIC_L2 ? 1 : 0,
+                                                      obj ? u.obj_part : nullptr);
+    NRB_LAUNCH_CHECK();
+    km_finish_kernel<<<k, 256, 0, st>>>(u.partial, u.chunk_base, u.offsets, kp, d, k, centroids, hassign,
+                                        obj ? u.obj_part : nullptr, obj ? obj_out : nullptr);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_km_split(int d, int k, int64_t n, float* hassign, float* centroids, double* stats, cudaStream_t st) {
+    km_split_kernel<<<1, 1024, 0, st>>>(d, k, n, hassign, centroids, stats);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+}  // namespace nrb
+
+extern "C" size_t nrb_kmeans_update_workspace(int64_t n, int32_t k, int32_t kp) {
+    return nrb::kmeans_update_ws(n, k, kp);
 }
 
 extern "C" int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32_t kp,
@@ -974,27 +1247,18 @@ extern "C" int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32
                                  void* stream) {
     NRB_REQUIRE(n >= 0 && n < (1LL << 31) && k > 0 && d > 0 && kp >= d && kp % 32 == 0 && kp <= 2048,
                 "kmeans_update: bad sizes n=%lld k=%d d=%d kp=%d", (long long)n, k, d, kp);
-    if (workspace_bytes < nrb_kmeans_update_workspace(n, k)) {
+    if (workspace_bytes < nrb_kmeans_update_workspace(n, k, kp)) {
         set_error("kmeans_update: workspace too small");
         return NRB_ERR_WORKSPACE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    char* w = (char*)workspace;
-    const size_t cs = counting_sort_ws(n, k);
-    int* offsets = (int*)(w + cs);
-    int* order = (int*)(w + cs + align_up((size_t)(k + 2) * sizeof(int), 256));
-    int rc = launch_counting_sort_i64(assign, n, k, offsets, order, nullptr, w, cs, st);
-    if (rc) return rc;
-    constexpr int RS = 4;
-    const int threads = (kp / 4) * RS;
-    NRB_REQUIRE(threads <= 1024, "kmeans_update: kp %d too large", kp);
-    const size_t smem = (size_t)RS * kp * sizeof(double);
-    if (smem > 48 * 1024)
-        NRB_CUDA_CHECK(cudaFuncSetAttribute(kmeans_update_kernel<RS>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kmeans_update_kernel<RS><<<k, threads, smem, st>>>(x_raw, kp, d, offsets, order, centroids, hassign);
-    NRB_LAUNCH_CHECK();
-    return NRB_OK;
+    return nrb::launch_kmeans_update(x_raw, n, d, kp, assign, k, centroids, hassign, workspace, nullptr, 0, nullptr,
+                                     (cudaStream_t)stream);
+}
+
+extern "C" int nrb_split_clusters(int32_t d, int32_t k, int64_t n, float* hassign, float* centroids, double* stats3,
+                                  void* stream) {
+    NRB_REQUIRE(hassign && centroids && stats3 && d > 0 && k > 0 && n > k, "split_clusters: bad arguments");
+    return nrb::launch_km_split(d, k, n, hassign, centroids, stats3, (cudaStream_t)stream);
 }
 
 extern "C" int nrb_merge_topk(const float* Dp, const int64_t* Ip, int32_t nparts, int64_t nq,

@@ -30,6 +30,8 @@ __all__ = [
 ]
 
 _FLT_MAX = 3.4028234663852886e38
+SMALL_NQ = 20  # faiss's distance_compute_blas_threshold: below it faiss itself leaves the GEMM route
+IVF_SMALL_NQ = 64  # IVF batches up to this size take the HBM-regime list scan (nrb_ivf_scan_small)
 IVF_QUERY_BATCH = 131072  # queries per nrb_ivf_search call (bounds the regrouped query planes and partial rows: ~8 GB at nprobe 16, k 50)
 
 
@@ -259,7 +261,9 @@ class IndexFlat:
         # else 3xTF32 (PATH_TC); PATH_TC1 = the same filter on the tf32 hi planes, PATH_TC forces
         # 3xTF32, PATH_SIMT the fp32 CUDA-core kernels
         self.path = PATH_AUTO
+        self.small_nq = SMALL_NQ  # batches below this take the low-latency exact path (0 disables it)
         self._xb: PackedMatrix | None = None
+        self._struct_cache = None
 
     @property
     def ntotal(self) -> int:
@@ -274,10 +278,44 @@ class IndexFlat:
         if self._xb is None:
             self._xb = PackedMatrix(self.d, t.device, planes=_INDEX_PLANES, track_max_norm=True)
         self._xb.append(t)
+        self._struct_cache = None
 
     def reset(self):
         if self._xb is not None:
             self._xb.clear()
+        self._struct_cache = None
+
+    def _struct(self) -> Matrix:
+        """struct nrb_matrix of the stored rows, cached between add() calls (the per-call cost of
+        the low-latency path is a handful of microseconds; rebuilding six tensor views is not)."""
+        if self._struct_cache is None:
+            self._struct_cache = self._packed().struct()
+        return self._struct_cache
+
+    def _search_small_host(self, a: np.ndarray, k: int, D=None, I=None):
+        """nq < 20, numpy in / numpy out (the call Retrieval.py:32 makes 50,000 times with nq = 1):
+        ONE C-ABI call -- staged H2D, the row-per-warp fp32 kernels, D2H, one sync."""
+        nq = a.shape[0]
+        if D is None:
+            D = np.empty((nq, k), dtype=np.float32)
+        if I is None:
+            I = np.empty((nq, k), dtype=np.int64)
+        assert D.shape == (nq, k) and I.shape == (nq, k) and D.dtype == np.float32 and I.dtype == np.int64
+        assert D.flags.c_contiguous and I.flags.c_contiguous, "bad output array"
+        check(lib.nrb_search_small_host(C.byref(self._struct()), a.ctypes.data, nq, self.d, self.metric_type, k, 0,
+                                        D.ctypes.data, I.ctypes.data, _stream()), "search_small_host")
+        return D, I
+
+    def _search_small_dev(self, t: torch.Tensor, k: int, id_base: int = 0):
+        """The same route for a CUDA tensor batch: asynchronous on the current stream."""
+        nq = t.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=t.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=t.device)
+        wsb = lib.nrb_search_small_workspace(nq, self.ntotal, k)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=t.device)
+        check(lib.nrb_search_small(t.data_ptr(), t.stride(0), nq, self.d, C.byref(self._struct()), self.metric_type, k,
+                                   id_base, D.data_ptr(), I.data_ptr(), ws.data_ptr(), wsb, _stream()), "search_small")
+        return D, I
 
     def _packed(self) -> PackedMatrix:
         if self._xb is None:
@@ -298,13 +336,21 @@ class IndexFlat:
         assert k > 0
         if k > _lib.MAX_K:
             raise RuntimeError(f"k={k} > {_lib.MAX_K} is not supported by the selection stage")
+        small = self.small_nq and self.path == PATH_AUTO and 0 < self.ntotal
         if not isinstance(x, torch.Tensor) and torch.cuda.is_available():
             a = np.ascontiguousarray(x, dtype=np.float32)
             assert a.ndim == 2 and a.shape[1] == self.d
+            if small and 0 < a.shape[0] < self.small_nq:
+                return self._search_small_host(a, int(k), D, I)
             if a.shape[0] >= 2 * _wave_rows():
                 return self._search_host_pipelined(a, int(k), D, I)
         t, from_np = _to_device_f32(x)
         assert t.shape[1] == self.d
+        if small and 0 < t.shape[0] < self.small_nq:
+            Dd, Id = self._search_small_dev(t, int(k))
+            if from_np or D is not None or I is not None:
+                return _to_host_pair(Dd, Id, D, I)
+            return Dd, Id
         q = PackedMatrix.from_tensor(t, planes=self._query_planes(int(k)))
         Dd, Id = self.search_packed(q, int(k))
         if from_np or D is not None or I is not None:
@@ -435,7 +481,7 @@ def kmeans_update(x: PackedMatrix, assign: torch.Tensor, k: int):
     """One centroid update (K1b): returns (centroids f32[k,d], hassign f32[k]) CUDA tensors."""
     cent = torch.empty((k, x.d), dtype=torch.float32, device=x.device)
     hassign = torch.empty((k,), dtype=torch.float32, device=x.device)
-    wsb = lib.nrb_kmeans_update_workspace(x.n, k)
+    wsb = lib.nrb_kmeans_update_workspace(x.n, k, x.kp)
     ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
     check(lib.nrb_kmeans_update(x.raw.data_ptr(), x.n, x.d, x.kp, assign.data_ptr(), k, cent.data_ptr(),
                                 hassign.data_ptr(), ws.data_ptr(), wsb, _stream()), "kmeans_update")
@@ -481,42 +527,51 @@ class Clustering(ClusteringParameters):
             index.reset()
             index.add(t)
             return
-        xs = PackedMatrix.from_tensor(t)
+        # rows for the assignment kernel: scaled fp16 plane (fp16 filter + exact refine) when d <= 256,
+        # else tf32 hi / lo planes (3xTF32)
+        xs = PackedMatrix.from_tensor(t, planes=("raw", "norms", "h16") if _round_kp(d) <= 256 else ("raw", "hi", "lo", "norms"))
+        x_max_norm = float(xs.norms[:n].max().sqrt())  # the one host read before the loop: sizes the filter margin
         best = None
         for redo in range(self.nredo):
             perm = rand_perm(n, self.seed + 1 + redo * 15486557)[:k]
             cent = t.index_select(0, torch.from_numpy(perm.astype(np.int64)).to(dev)).contiguous()
             if self.spherical:
                 check(lib.nrb_normalize_l2(cent.data_ptr(), k, d, d, _stream()), "normalize_l2")
-            if index.ntotal != 0:
-                index.reset()
+            # the whole iteration loop is ONE C-ABI call queued on the stream (nrb_kmeans_train): pack
+            # centroids, K2 assignment (k = 1), objective, K1b update, device split_clusters; the only
+            # host synchronisation is the read of the per-iteration statistics at the end. A trace hook
+            # (teacher-forced parity tests) runs the same call one iteration at a time.
+            metric = index.metric_type
+            wsb = lib.nrb_kmeans_train_workspace(n, k, xs.kp)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            st_dev = torch.zeros((max(self.niter, 1), 4), dtype=torch.float64, device=dev)
+            xs_struct = xs.struct()
+            xs_struct.max_norm = x_max_norm
+            assign = torch.empty(n, dtype=torch.int64, device=dev) if self.trace is not None else None
+
+            def run(it0, its):
+                check(lib.nrb_kmeans_train(C.byref(xs_struct), k, its, metric, 1 if self.spherical else 0,
+                                           cent.data_ptr(), _ptr(assign), st_dev[it0:].data_ptr(), ws.data_ptr(), wsb,
+                                           _stream()), "kmeans_train")
+
+            if self.trace is None:
+                run(0, self.niter)
+            else:
+                for it in range(self.niter):
+                    cent_in = _to_host(cent)
+                    run(it, 1)
+                    self.trace(it, cent_in, _to_host(assign), _to_host(cent))
+            sh = _to_host(st_dev)
+            if (sh[: self.niter, 2] < 0).any():
+                raise RuntimeError("split_clusters: no cluster to split")
+            stats = [ClusteringIterationStats(float(np.float32(sh[it, 0])), float(sh[it, 1]), int(sh[it, 2]))
+                     for it in range(self.niter)]
+            obj = stats[-1].obj if stats else 0.0
+            if self.verbose:
+                for it, s_ in enumerate(stats):
+                    print("  Iteration %d objective=%g imbalance=%.3f nsplit=%d" % (it, s_.obj, s_.imbalance_factor, s_.nsplit))
+            index.reset()
             index.add(cent)
-            stats = []
-            obj = 0.0
-            for it in range(self.niter):
-                Dd, assign = index.search_packed(xs, 1)
-                assign = assign.reshape(-1)
-                obj_t = Dd.sum()
-                cent_in = cent
-                cent, hassign = kmeans_update(xs, assign, k)
-                hass = _to_host(hassign)
-                imb = float((hass.astype(np.float64) ** 2).sum() * k / float(n) ** 2)
-                nsplit = 0
-                if (hass == 0).any():
-                    ch = _to_host(cent)
-                    nsplit = check(lib.nrb_split_clusters_host(d, k, n, hass.ctypes.data, ch.ctypes.data),
-                                   "split_clusters")
-                    cent = torch.from_numpy(ch).to(dev)
-                if self.spherical:
-                    check(lib.nrb_normalize_l2(cent.data_ptr(), k, d, d, _stream()), "normalize_l2")
-                obj = float(obj_t)
-                stats.append(ClusteringIterationStats(obj, imb, nsplit))
-                if self.verbose:
-                    print("  Iteration %d objective=%g imbalance=%.3f nsplit=%d" % (it, obj, imb, nsplit))
-                if self.trace is not None:
-                    self.trace(it, _to_host(cent_in), _to_host(assign), _to_host(cent))
-                index.reset()
-                index.add(cent)
             if self.nredo > 1:
                 better = best is None or (obj > best[0] if index.metric_type == METRIC_INNER_PRODUCT
                                           else obj < best[0])
@@ -672,6 +727,17 @@ class IndexIVFFlat:
                                          (("raw", "norms", "h16") if filt else ()) +
                                          (("norms",) if self.metric_type == METRIC_L2 else ())))
             ls = L["packed"].struct()
+            if self.path == PATH_AUTO and nq <= IVF_SMALL_NQ and nq * nprobe <= 65535 and self.quantizer.ntotal:
+                # HBM-regime route for small batches: exact fp32 coarse search + row-per-warp list scan
+                _, coarse = self.quantizer._search_small_dev(t, nprobe) if nq < SMALL_NQ else \
+                    self.quantizer.search(t, nprobe)
+                wsb = lib.nrb_ivf_scan_small_workspace(nq, nprobe, L["max_len"], self.ntotal, int(k))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                check(lib.nrb_ivf_scan_small(t.data_ptr(), t.stride(0), nq, self.d, C.byref(ls), L["offsets"].data_ptr(),
+                                             self.nlist, L["max_len"], L["ids"].data_ptr(), coarse.data_ptr(), nprobe,
+                                             self.metric_type, int(k), D.data_ptr(), I.data_ptr(), ws.data_ptr(), wsb,
+                                             _stream()), "ivf_scan_small")
+                nq = 0  # done
             for q0 in range(0, nq, IVF_QUERY_BATCH):
                 q1 = min(nq, q0 + IVF_QUERY_BATCH)
                 q = PackedMatrix.from_tensor(t[q0:q1], planes=planes)

@@ -177,3 +177,18 @@ def test_flat_planner_invariants_and_known_plans():
                     assert p["full_pairs"] % (148 if path == SIMT else 74) == 0
     bad = (C.c_int32 * 10)()
     assert _lib.lib.nrb_plan_flat_describe(10, 10, 5, _lib.PATH_AUTO, bad) == -1
+
+
+def test_reference_script_fixtures_are_byte_identical():
+    """tests/fixtures/reference_scripts holds test DATA: copies of three reference scripts that the
+    GPU suite runs unmodified. They must match the recorded sha256 and, where /root/reference is
+    present (this container), the originals."""
+    import hashlib
+    import json
+    d = os.path.join(ROOT, "tests", "fixtures", "reference_scripts")
+    prov = json.load(open(os.path.join(d, "PROVENANCE.json")))
+    for name, meta in prov["files"].items():
+        b = open(os.path.join(d, name), "rb").read()
+        assert hashlib.sha256(b).hexdigest() == meta["sha256"] and len(b) == meta["bytes"]
+        if os.path.exists(meta["source"]):
+            assert open(meta["source"], "rb").read() == b

@@ -253,3 +253,67 @@ def test_ivf_golden_fixture(nf, metric, path):
     D, I = ivf.search(g["xq"], 10)
     rep = compare_topk(D, I, g[f"D{metric}"], g[f"I{metric}"], metric)
     assert rep["id_mismatch_queries"] == 0 and rep["score_violations"] == 0, rep
+
+
+def test_device_split_clusters_equals_host_routine(nf):
+    """km_split_kernel (std::mt19937(1234) restated on the device) against nrb_split_clusters_host:
+    same splits, same perturbed centroids, bit for bit; plus the imbalance factor."""
+    import torch
+    from newsrecommend_b200._lib import check, lib
+    rng = np.random.default_rng(5)
+    for k, d, n_empty in [(60, 16, 7), (300, 256, 1), (300, 250, 40), (1500, 32, 700), (50, 8, 0)]:
+        sizes = rng.integers(2, 400, size=k).astype(np.float32)
+        empty = rng.choice(k, size=n_empty, replace=False)
+        sizes[empty] = 0
+        n = int(sizes.sum())
+        cent = rng.standard_normal((k, d), dtype=np.float32)
+        cent[empty] = 0
+        h_host, c_host = sizes.copy(), cent.copy()
+        ns = check(lib.nrb_split_clusters_host(d, k, n, h_host.ctypes.data, c_host.ctypes.data))
+        h_dev, c_dev = torch.from_numpy(sizes.copy()).cuda(), torch.from_numpy(cent.copy()).cuda()
+        st = torch.zeros(4, dtype=torch.float64, device="cuda")
+        check(lib.nrb_split_clusters(d, k, n, h_dev.data_ptr(), c_dev.data_ptr(), st.data_ptr(), None))
+        st = st.cpu().numpy()
+        assert int(st[2]) == ns == n_empty
+        assert np.array_equal(h_dev.cpu().numpy(), h_host)
+        assert np.array_equal(c_dev.cpu().numpy(), c_host)
+        assert abs(st[1] - (sizes.astype(np.float64) ** 2).sum() * k / float(n) ** 2) <= 1e-12 * st[1]
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_fused_trainer_equals_stepwise_trainer(nf, metric):
+    """nrb_kmeans_train with niter = 10 in one call == ten calls with niter = 1 (what the trace
+    hook of the teacher-forced tests uses) == the same loop built from the separate entry points
+    (search k = 1, nrb_kmeans_update, host split_clusters): bit-identical centroids and stats."""
+    import torch
+    from newsrecommend_b200 import synth
+    from newsrecommend_b200._lib import check, lib
+    x = synth.g_skew(16_000, 250, 9, n_topics=80)  # <= 256 * k rows: no subsample, so the loop below sees the same rows
+    k, niter = 64, 10
+    outs = []
+    for stepwise in (False, True):
+        clus = nf.Clustering(250, k)
+        clus.niter = niter
+        if stepwise:
+            clus.trace = lambda it, cin, a, cout: None
+        index = nf.IndexFlatIP(250) if metric == 0 else nf.IndexFlatL2(250)
+        clus.train(x, index)
+        outs.append((clus.centroids.copy(), [(s.obj, s.imbalance_factor, s.nsplit) for s in clus.iteration_stats]))
+        assert index.ntotal == k and np.array_equal(index.reconstruct_n(0, k).reshape(-1), clus.centroids)
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    # the loop from the separate entry points
+    xt = torch.from_numpy(x).cuda()
+    p = nf.PackedMatrix.from_tensor(xt)
+    perm = nf.rand_perm(x.shape[0], 1235)[:k]
+    cent = xt[torch.from_numpy(perm.astype(np.int64)).cuda()].contiguous()
+    for it in range(niter):
+        index = nf.IndexFlat(250, metric)
+        index.path = nf.PATH_TC
+        index.add(cent)
+        _, a = index.search_packed(p, 1)
+        cent, h = nf.kmeans_update(p, a.reshape(-1), k)
+        hh, ch = h.cpu().numpy(), cent.cpu().numpy()
+        if (hh == 0).any():
+            check(lib.nrb_split_clusters_host(250, k, x.shape[0], hh.ctypes.data, ch.ctypes.data))
+            cent = torch.from_numpy(ch).cuda()
+    assert np.array_equal(cent.cpu().numpy().reshape(-1), outs[0][0])
