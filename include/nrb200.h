@@ -249,6 +249,10 @@ int nrb_ivf_scan_small(const float* xq, int64_t ldq, int32_t nq, int32_t d, cons
                        const int64_t* coarse, int32_t nprobe, int32_t metric, int32_t k, float* D, int64_t* I,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Retrieval.py:6-8 on the device: table f64[n, width] = embedding values followed by
+ * the article id (news/article_table.npy) -> emb f32[n, width-1] C-contiguous, ids i64[n]. */
+int nrb_split_table_f64(const double* table, int64_t n, int32_t width, float* emb, int64_t* ids, void* stream);
+
 /* Wire format of the all-to-all by query range (the exchange step of the catalog-sharded search):
  * P[i] = (fp32 bits of D[i]) << 32 | uint32(I[i] - id_base), 0xffffffff in the low word when
  * I[i] < 0. 8 bytes per candidate, one collective instead of two. n = nq * k elements. */

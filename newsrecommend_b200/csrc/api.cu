@@ -130,7 +130,8 @@ static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
     // tile, 148 slots instead of 74) can sometimes be cut one step finer than CTA pairs, e.g.
     // 49 tiles x 3 chunks = 147 units where 25 pairs stop at 2 chunks. CTA pairs halve the L2
     // traffic per unit of work, so they stay unless the single-CTA plan is clearly shorter.
-    if (path == NRB_PATH_TC16 && p.full_pairs == 0 && p.nqt <= sm_count() && !getenv("NRB_NO_SINGLE_CTA")) {
+    // (catalogs of one tile -- coarse quantizers -- go to the CTA-pair short-unit kernel instead)
+    if (path == NRB_PATH_TC16 && p.full_pairs == 0 && p.nqt <= sm_count() && nb > 256 && !getenv("NRB_NO_SINGLE_CTA")) {
         const int C1 = sm_count();
         static const double ov_tiles1 = getenv("NRB_FLAT_OV_TILES") ? atof(getenv("NRB_FLAT_OV_TILES")) : 200.0;
         const double ov = ov_tiles1 / nbt;
@@ -599,7 +600,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
                                  w.part_idx, w.part_cnt, w.flags, w.scratch, w.scratch_bytes, w.gthr, nullptr, 1,
-                                 path == NRB_PATH_TC16, p.single, st);
+                                 path == NRB_PATH_TC16, p.single, (!p.single && b->n <= 256) ? 1 : 0, st);  // <= 256 items: every unit is one tile (coarse search, nearest centroid) -> the short-unit kernel
     }
     if (rc) return rc;
     if ((rc = launch_gather_refine(w.part_key, w.part_idx, w.part_cnt, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
@@ -697,6 +698,13 @@ extern "C" size_t nrb_ivf_search_workspace(int64_t nq, int32_t nprobe, int32_t k
 }
 
 namespace nrb {
+
+// phase A (or a single-phase scan): cold rows; phase B: rows start from their query's shared bound
+static inline int ivf_mode_of(int nph, int i) {
+    static const int force = getenv("NRB_IVF_MODE") ? atoi(getenv("NRB_IVF_MODE")) : -1;  // A/B measurements
+    if (force >= 0) return force;
+    return (nph > 1 && i == 1) ? 2 : 1;
+}
 
 // dst[i, :] = src[list[i], :] for rows of `width` 64-bit ids (coarse assignments of flagged queries)
 __global__ void gather_i64_rows_kernel(const int64_t* __restrict__ src, int width, const int* __restrict__ list,
@@ -799,7 +807,7 @@ static int ivf_search_impl(const nrb_matrix* q, const nrb_matrix* lists, const i
         else
             rc = launch_topk_tc1_dev(&g[i], lists, v.units, v.n_units, f.grid, metric, k, pw, 2.f * eps_xmax, w.part_key + po,
                                      w.part_idx + po, w.part_cnt + f.prow_base, w.flags, w.scratch, w.scratch_bytes, w.gthr,
-                                     v.order, f.ncols, 1, 0, st);
+                                     v.order, f.ncols, 1, 0, ivf_mode_of(p.nph, i), st);
         if (rc) return rc;
     }
     // ---- 5. per query: merge (sorted partial rows) or gather + exact refine (filter)

@@ -184,6 +184,63 @@ __global__ void cs_scan_kernel(int* __restrict__ chunk_hist, int nchunks, int nb
     }
 }
 
+// The same scan for long inputs (thousands of chunks: the (query, list) pairs of an IVF batch), in
+// three small grids instead of one block walking every chunk twice: the chunks are cut into
+// CS_GROUPS groups; (1) per-group bucket totals, (2) one block: exclusive scan over (bucket, group) +
+// the bucket offsets, (3) per group: the chunks' exclusive prefixes.
+constexpr int CS_GROUPS = 64;
+__global__ void cs_group_tot_kernel(const int* __restrict__ chunk_hist, int nchunks, int nb1, int* __restrict__ gtot) {
+    const int g = blockIdx.x, per = (nchunks + CS_GROUPS - 1) / CS_GROUPS;
+    const int c0 = g * per, c1 = min(nchunks, c0 + per);
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) {
+        int s = 0;
+        for (int c = c0; c < c1; c++) s += chunk_hist[(int64_t)c * nb1 + b];
+        gtot[g * nb1 + b] = s;
+    }
+}
+__global__ void cs_group_scan_kernel(int* __restrict__ gtot, int nb, int* __restrict__ offsets) {
+    extern __shared__ int tot[];  // nb + 2
+    const int nb1 = nb + 1;
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) {
+        int s = 0;
+        for (int g = 0; g < CS_GROUPS; g++) s += gtot[g * nb1 + b];
+        tot[b] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nb1; b++) {
+            int t = tot[b];
+            tot[b] = run;
+            run += t;
+        }
+        tot[nb1] = run;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= nb; b += blockDim.x) offsets[b] = tot[b];
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) {
+        int run = tot[b];
+        for (int g = 0; g < CS_GROUPS; g++) {
+            const int t = gtot[g * nb1 + b];
+            gtot[g * nb1 + b] = run;
+            run += t;
+        }
+    }
+}
+__global__ void cs_group_prefix_kernel(int* __restrict__ chunk_hist, int nchunks, int nb1, const int* __restrict__ gtot) {
+    const int g = blockIdx.x, per = (nchunks + CS_GROUPS - 1) / CS_GROUPS;
+    const int c0 = g * per, c1 = min(nchunks, c0 + per);
+    for (int b = threadIdx.x; b < nb1; b += blockDim.x) {
+        int run = gtot[g * nb1 + b];
+        for (int c = c0; c < c1; c++) {
+            const int64_t o = (int64_t)c * nb1 + b;
+            const int t = chunk_hist[o];
+            chunk_hist[o] = run;
+            run += t;
+        }
+    }
+}
+
 template <typename KeyT>
 __global__ void cs_scatter_kernel(const KeyT* __restrict__ key, int64_t n, int nb,
                                   const int* __restrict__ chunk_base, int* __restrict__ order,
@@ -1051,10 +1108,11 @@ int launch_fill_flat_units_single(Unit* units, int* n_units_out, int* src, int64
     return NRB_OK;
 }
 
+size_t counting_sort_ws(int64_t n, int nb);
 int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets, int* order,
                              int* pos_of, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int nchunks = (int)((n + CS_CHUNK - 1) / CS_CHUNK);
-    const size_t need = (size_t)(nchunks > 0 ? nchunks : 1) * (nb + 1) * sizeof(int);
+    const size_t need = counting_sort_ws(n, nb);
     if (ws_bytes < need) {
         set_error("counting sort: workspace %zu < %zu", ws_bytes, need);
         return NRB_ERR_WORKSPACE;
@@ -1066,8 +1124,18 @@ int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets
         cs_hist_kernel<int64_t><<<nchunks, CS_THREADS, sh, st>>>(key, n, nb, chunk_hist);
         NRB_LAUNCH_CHECK();
     }
-    cs_scan_kernel<<<1, 512, sh, st>>>(chunk_hist, nchunks, nb, offsets);
-    NRB_LAUNCH_CHECK();
+    if (nchunks > 4 * CS_GROUPS) {
+        int* gtot = chunk_hist + (size_t)nchunks * (nb + 1);
+        cs_group_tot_kernel<<<CS_GROUPS, 256, 0, st>>>(chunk_hist, nchunks, nb + 1, gtot);
+        NRB_LAUNCH_CHECK();
+        cs_group_scan_kernel<<<1, 512, sh, st>>>(gtot, nb, offsets);
+        NRB_LAUNCH_CHECK();
+        cs_group_prefix_kernel<<<CS_GROUPS, 256, 0, st>>>(chunk_hist, nchunks, nb + 1, gtot);
+        NRB_LAUNCH_CHECK();
+    } else {
+        cs_scan_kernel<<<1, 512, sh, st>>>(chunk_hist, nchunks, nb, offsets);
+        NRB_LAUNCH_CHECK();
+    }
     if (nchunks > 0) {
         cs_scatter_kernel<int64_t><<<nchunks, CS_THREADS, sh, st>>>(key, n, nb, chunk_hist, order, pos_of);
         NRB_LAUNCH_CHECK();
@@ -1077,7 +1145,7 @@ int launch_counting_sort_i64(const int64_t* key, int64_t n, int nb, int* offsets
 
 size_t counting_sort_ws(int64_t n, int nb) {
     const int64_t nchunks = (n + CS_CHUNK - 1) / CS_CHUNK;
-    return align_up((size_t)(nchunks > 0 ? nchunks : 1) * (nb + 1) * sizeof(int), 256);
+    return align_up((size_t)((nchunks > 0 ? nchunks : 1) + CS_GROUPS) * (nb + 1) * sizeof(int), 256);
 }
 
 }  // namespace nrb
@@ -1311,6 +1379,36 @@ extern "C" int nrb_merge_topk_packed(const uint64_t* P, const int64_t* bases, in
         shard_merge_packed_kernel<4><<<blocks, wpb * 32, 0, st>>>(ss, bases, D, I);
     else
         shard_merge_packed_kernel<8><<<blocks, wpb * 32, 0, st>>>(ss, bases, D, I);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+// ------------------------------------------------------------------- article table
+// Retrieval.py:6-8 on the device: news/article_table.npy is a float64 table whose rows are the
+// embedding values followed by the article id. One pass: ids[i] = (int64) t[i, w-1],
+// emb[i, :] = (float) t[i, :w-1] (C-contiguous, row stride w-1) -- the two .astype() copies and
+// np.ascontiguousarray of the script as one HBM-bound kernel (reads n*w*8 bytes).
+__global__ void split_table_f64_kernel(const double* __restrict__ t, int64_t n, int w, float* __restrict__ emb,
+                                       int64_t* __restrict__ ids) {
+    const int d = w - 1;
+    const int64_t total = n * (int64_t)w;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / w;
+        const int c = (int)(e - i * w);
+        const double v = t[e];
+        if (c == d)
+            ids[i] = (int64_t)v;
+        else
+            emb[i * d + c] = (float)v;
+    }
+}
+
+extern "C" int nrb_split_table_f64(const double* table, int64_t n, int32_t width, float* emb, int64_t* ids, void* stream) {
+    NRB_REQUIRE(n >= 0 && width >= 2 && (n == 0 || (table && emb && ids)), "split_table_f64: bad arguments");
+    if (n == 0) return NRB_OK;
+    int64_t blocks = (n * width + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_table_f64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, n, width, emb, ids);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }

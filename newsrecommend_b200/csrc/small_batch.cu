@@ -570,7 +570,7 @@ static int small_flat_launch(const float* xq, int64_t ldq, int nq, int d, const 
         small_scores_kernel<4, L2, 4><<<dim3(small_grid_rows(n, 4), 1), SMALL_THREADS, 4 * kp * sizeof(float), st>>>(
             xq, ldq, nq, d, b->raw, b->n, kp, w.scores);
     } else {
-        small_scores_kernel<SMALL_QG, L2, 2><<<dim3(small_grid_rows(n, 2), (nq + SMALL_QG - 1) / SMALL_QG), SMALL_THREADS,
+        small_scores_kernel<SMALL_QG, L2, 4><<<dim3(small_grid_rows(n, 4), (nq + SMALL_QG - 1) / SMALL_QG), SMALL_THREADS,
                                                SMALL_QG * kp * sizeof(float), st>>>(xq, ldq, nq, d, b->raw, b->n, kp, w.scores);
     }
     NRB_LAUNCH_CHECK();

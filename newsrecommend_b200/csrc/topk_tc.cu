@@ -549,6 +549,109 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
     }
 }
 
+// One-tile units from a cold start: the coarse-quantizer search and the nearest-centroid assignment
+// (every query x at most 256 centroids), and the short lists of an IVF scan. The generic path would
+// append the whole tile to the candidate buffers (every key beats a threshold of -inf) and then prune
+// 250 entries per row -- ~200k cycles for 16 MMAs. Here the warp keeps its 32 rows x 128 columns in
+// registers, and every THREAD bisects on its own row: 16 halvings of [row min, row max], the count of
+// keys >= mid summed with the partner warp's (the other 128 columns of the same rows) through shared
+// memory, one 64-thread named barrier per round. lo ends as a lower bound of the row's k-th best key
+// with count(>= lo) >= k; keys >= lo - margin are appended (the margin set the refine stage needs).
+// Returns with st.cnt entries in the row's buffer; *lb_out = lo (unscaled key domain), NEG_INF if the
+// row has fewer than k columns.
+struct OneShotOut {
+    int cnt;
+    float lb;
+};
+// Behind a real call: the routine wants ~150 registers for the row's 128 keys; inlined into the
+// epilogue (which ptxas allocates at the kernel's 168-register bound) the keys spilled to local
+// memory. As a call, the caller's live state is saved once around it instead.
+template <bool L2, bool PAIR>
+__device__ __noinline__ OneShotOut single_tile_call(uint32_t taddr0, int valid, int id0, const float* nrm, float sc,
+                                                    float inv, float qn, float margin, float* myk, int* myi, int k,
+                                                    XchgShared* xs, int wg, int row, int quad, uint32_t tempty_remote,
+                                                    uint64_t* tempty_local) {
+    const int lane = threadIdx.x & 31;
+    float f[HALF_N];
+    {
+        uint32_t v[4][32];
+        ptx::tmem_ld_32x32b_x32(taddr0, v[0]);
+        ptx::tmem_ld_32x32b_x32(taddr0 + 32, v[1]);
+        ptx::tmem_ld_32x32b_x32(taddr0 + 64, v[2]);
+        ptx::tmem_ld_32x32b_x32(taddr0 + 96, v[3]);
+        ptx::tmem_ld_wait();
+        // hand the accumulator back to the MMA warp
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (PAIR)
+                ptx::mbar_arrive_cluster_relaxed(tempty_remote);
+            else
+                ptx::mbar_arrive(tempty_local);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int i = 0; i < 32; i++) f[c * 32 + i] = __uint_as_float(v[c][i]);  // IP: the accumulator's (scaled) domain
+    }
+    const float m2inv = -2.f * inv;
+    float mn = __builtin_huge_valf(), mx = NEG_INF;
+#pragma unroll
+    for (int i = 0; i < HALF_N; i++) {
+        float x = f[i];
+        if (L2) x = -fmaxf(fmaf(x, m2inv, qn + nrm[i]), 0.f);
+        const bool ok = i < valid;
+        f[i] = ok ? x : NEG_INF;
+        mn = ok ? fminf(mn, x) : mn;
+        mx = ok ? fmaxf(mx, x) : mx;
+    }
+    const int nv = valid < 0 ? 0 : (valid > HALF_N ? HALF_N : valid);
+    // exchange (min, max, valid columns) with the partner warp: the same rows, the other column half
+    xs->thr[wg][row] = mn;
+    xs->cnt[wg][row] = nv;
+    xs->fresh[wg][row] = __float_as_int(mx);
+    ptx::named_bar_sync(3 + quad, 64);
+    float lo = fminf(mn, xs->thr[wg ^ 1][row]);
+    float hi = fmaxf(mx, __int_as_float(xs->fresh[wg ^ 1][row]));
+    const int ntot = nv + xs->cnt[wg ^ 1][row];
+    ptx::named_bar_sync(3 + quad, 64);
+    const bool enough = ntot >= k;
+    // invariant: count(>= lo) >= k. 16 rounds leave (max - min) / 65536 of slack below the k-th key. Rows
+    // with fewer than k columns keep everything but still meet the partner at every barrier.
+#pragma unroll 1
+    for (int r = 0; r < 16; r++) {
+        const float mid = lo + 0.5f * (hi - lo);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < HALF_N; i++) c += (f[i] >= mid) ? 1 : 0;
+        int* slot = (r & 1) ? xs->fresh[wg] : xs->cnt[wg];
+        const int* pslot = (r & 1) ? xs->fresh[wg ^ 1] : xs->cnt[wg ^ 1];
+        slot[row] = c;
+        ptx::named_bar_sync(3 + quad, 64);
+        const int tot = c + pslot[row];
+        if (tot >= k && mid > lo)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    // margin in the domain of f (IP keys carry the row's scale)
+    const float cut = enough ? lo - (L2 ? margin : margin * sc) : NEG_INF;
+    const float ksc = L2 ? 1.f : inv;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < HALF_N; i++) {
+        if (f[i] >= cut && i < valid) {
+            myk[cnt] = f[i] * ksc;
+            myi[cnt] = id0 + i;
+            cnt++;
+        }
+    }
+    OneShotOut o;
+    o.cnt = cnt;
+    o.lb = enough ? lo * ksc : NEG_INF;
+    return o;
+}
+
 template <bool L2>
 __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms, const Unit& un, int col_base,
                                                 int valid, int64_t b_total, int etid, int wg) {
@@ -590,9 +693,17 @@ struct EpiArgs {
     // fp16 filter: accumulator = a_row_scale[row] * b_scale * (q . x), powers of two (null / 1: unscaled)
     const float* a_row_scale;
     float b_scale;
+    // IVF phase B (every row starts from the bound its query's closest list established): units shorter
+    // than HOT_MIN_TILES skip the scheduled prunes, and a unit ends without the pairwise union prune
+    // (rows over pw entries are tightened one by one; the in-tile overflow guard stays)
+    int hot;
+    int one_shot_ok;  // 1: one-tile units take epi_single_tile (0 only for A/B measurements: NRB_NO_ONE_SHOT)
 };
+constexpr int HOT_MIN_TILES = 16;
 
-template <bool L2, bool PAIR, bool NEED_QN>
+// IVFX compiles in the short-unit machinery (hot rows, one-tile units): only the double-buffered
+// kernel (topk_tc3d_kernel) carries it, so the flat search kernels keep their exact code.
+template <bool L2, bool PAIR, bool NEED_QN, bool IVFX = false>
 __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, uint64_t* tempty,
                                              float (*nrm)[2][HALF_N], XchgShared* xs, uint32_t tmem_base, int warp,
                                              int lane, uint32_t rank) {
@@ -633,6 +744,9 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         st.flag = 0;
         st.gslot = nullptr;
         if (A.gthr && live) st.gslot = A.gthr + (A.row_map ? A.row_map[ar] / A.row_div : (int)ar);
+        // filter kernels, one-tile unit, cold rows: per-thread bisection in registers (epi_single_tile)
+        const bool hot = IVFX && A.hot;
+        const bool one_shot = IVFX && NEED_QN && !hot && ntiles == 1 && A.one_shot_ok;
         for (int t = 0; t < ntiles; t++, gt++) {
             const int acc = (int)(gt & 1);
             const uint32_t acc_phase = (gt >> 1) & 1;
@@ -666,7 +780,15 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                         ptx::mbar_arrive(&tempty[acc]);
                 }
             };
-            if (valid >= HALF_N) {
+            if (IVFX && one_shot) {
+                const OneShotOut o = single_tile_call<L2, PAIR>(taddr0, valid, un.b_row0 + col_base, nrm_t, st.sc, st.inv, st.qn,
+                                                              st.margin, myk, myi, A.k, xs, wg, row, quad,
+                                                              acc ? tempty_remote1 : tempty_remote0, &tempty[acc]);
+                st.cnt = o.cnt;
+                st.base = o.cnt;
+                NRB_TR(warp - EPI_WARP0 + 1, gt, 2);
+                if (wg == 0 && st.gslot && o.lb > NEG_INF) atomicMax(st.gslot, ordered_u32(o.lb));
+            } else if (valid >= HALF_N) {
                 // Full tile: copy the warp's 32 x 128 scores into registers and give the accumulator
                 // back BEFORE selecting. The selection time of a tile varies from warp to warp (it
                 // depends on how many keys pass), and the MMA warp needs all 16 warps of the CTA
@@ -699,7 +821,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             // half) do it together on the union of their buffers: see union_tighten_rows.
             NRB_TR(warp - EPI_WARP0 + 1, gt, 3);
             const uint32_t tp = (uint32_t)t + 1u;
-            if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles) {
+            if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles && !(hot && ntiles < HOT_MIN_TILES)) {
                 xs->cnt[wg][row] = st.cnt;
                 xs->fresh[wg][row] = st.cnt - st.base;
                 xs->thr[wg][row] = st.thr;
@@ -724,7 +846,18 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 }
             }
         }
-        if (NEED_QN) {
+        if (IVFX && NEED_QN && (hot || one_shot)) {
+            // hot units: rows hold a handful of entries; only rows over pw are tightened, each on its own
+            // (no exchange with the partner warp, no barriers), then the rows leave unsorted
+            const unsigned need = __ballot_sync(0xffffffffu, st.cnt > A.pw);
+            if (need) epi_prune_rows<L2>(need, st, ck, ci, A.k, A.pw, lane);
+            if (st.cnt > A.pw) {
+                st.flag = 1;
+                st.cnt = A.pw;
+            }
+            epi_unit_end_unsorted(live ? st.cnt : 0, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.pw,
+                                  A.part_key, A.part_idx, A.part_cnt, lane);
+        } else if (NEED_QN) {
             // final union prune (rows that need one only), then the rows leave unsorted
             xs->cnt[wg][row] = st.cnt;
             xs->fresh[wg][row] = st.cnt - st.base;
@@ -877,7 +1010,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         // ------------------------------------------------------------------ selection epilogue
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, 0);
     }
 
@@ -1017,7 +1150,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
@@ -1054,8 +1187,8 @@ struct Tc3Shared {
     uint64_t empty[STAGES];
     uint64_t tfull[2];
     uint64_t tempty[2];
-    uint64_t afull;
-    uint64_t aempty;
+    uint64_t afull[2];
+    uint64_t aempty[2];
     uint32_t tmem_base;
     uint32_t pad;
     float nrm[EPI_WGS][2][HALF_N];
@@ -1078,15 +1211,22 @@ static_assert(v3_smem<false>() <= 232448 && v3_smem<true>() <= 232448,
 // batches that are a single partial wave, where an odd number of query tiles or a phantom tile
 // keeps CTA pairs from cutting the catalog finely enough to use every SM (e.g. 49 tiles x 3
 // chunks = 147 units fill 147 of 148 SMs; 25 pairs can only be cut 2 ways = 50 of 74 pairs).
-template <bool F16, bool PAIR>
+// A2 = two resident query tiles (fp16 CTA pairs only): the producer loads the NEXT unit's query tile
+// while the current unit computes, which takes the query-tile load (and the drain of the previous
+// unit's MMAs it had to wait for) off the critical path between units. It pays when units are
+// short -- the (list, 256 queries) units of an IVF scan average a few item tiles -- and costs three
+// item stages (5 instead of 8), so the flat search keeps the single-buffer form.
+template <bool F16, bool PAIR, bool A2 = false>
 struct Tc3Lay {
+    static constexpr int NA = A2 ? 2 : 1;
     static constexpr int B_STAGE_BYTES = PAIR ? BH_BYTES : B_BYTES;
-    static constexpr int STAGES = PAIR ? Tc3Cfg<F16>::STAGES : Tc3Cfg<F16>::STAGES / 2;
-    static constexpr size_t SMEM = (size_t)Tc3Cfg<F16>::A_TILE_BYTES + (size_t)STAGES * B_STAGE_BYTES + sizeof(Tc3Shared<STAGES>);
+    static constexpr int STAGES = A2 ? 5 : (PAIR ? Tc3Cfg<F16>::STAGES : Tc3Cfg<F16>::STAGES / 2);
+    static constexpr size_t SMEM = (size_t)NA * Tc3Cfg<F16>::A_TILE_BYTES + (size_t)STAGES * B_STAGE_BYTES + sizeof(Tc3Shared<STAGES>);
 };
 static_assert(Tc3Lay<true, false>::SMEM <= 232448, "single-CTA filter kernel exceeds the shared memory per CTA");
+static_assert(Tc3Lay<true, true, true>::SMEM <= 232448, "double-buffered filter kernel exceeds the shared memory per CTA");
 
-template <bool L2, bool F16, bool PAIR>
+template <bool L2, bool F16, bool PAIR, bool A2 = false>
 __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtensorMap& map_bh,
                                          const Unit* __restrict__ units, const int* __restrict__ n_units_p, int nkc,
                                          int k, int pw, float margin_scale, const float* __restrict__ a_norms,
@@ -1096,14 +1236,16 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
                                          float* __restrict__ cand_key_buf,
                                          int* __restrict__ cand_idx_buf, unsigned* __restrict__ gthr,
                                          const float* __restrict__ a_row_scale, float b_scale,
-                                         const int* __restrict__ row_map, int row_div) {
-    constexpr int STAGES = Tc3Lay<F16, PAIR>::STAGES;
-    constexpr int BSB = Tc3Lay<F16, PAIR>::B_STAGE_BYTES;
+                                         const int* __restrict__ row_map, int row_div, int hot) {
+    constexpr int STAGES = Tc3Lay<F16, PAIR, A2>::STAGES;
+    constexpr int BSB = Tc3Lay<F16, PAIR, A2>::B_STAGE_BYTES;
+    constexpr int NA = Tc3Lay<F16, PAIR, A2>::NA;
+    constexpr int ATB = Tc3Cfg<F16>::A_TILE_BYTES;
     constexpr int KE = F16 ? 2 * KC : KC;  // elements per 128-byte K chunk
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;  // 128-byte swizzled tiles need 1024-byte alignment
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* smem_b = smem + Tc3Cfg<F16>::A_TILE_BYTES;
+    uint8_t* smem_b = smem + (size_t)NA * ATB;
     Tc3Shared<STAGES>* sh = reinterpret_cast<Tc3Shared<STAGES>*>(smem_b + (size_t)STAGES * BSB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1122,8 +1264,10 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
             ptx::mbar_init(&sh->tfull[a], 1);
             ptx::mbar_init(&sh->tempty[a], PAIR ? 16 : 8);
         }
-        ptx::mbar_init(&sh->afull, 1);
-        ptx::mbar_init(&sh->aempty, 1);
+        for (int a = 0; a < 2; a++) {
+            ptx::mbar_init(&sh->afull[a], 1);
+            ptx::mbar_init(&sh->aempty[a], 1);
+        }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&map_ah);
         ptx::prefetch_tensormap(&map_bh);
@@ -1151,27 +1295,30 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (every CTA)
         const uint32_t full0_base = PAIR ? ptx::mapa_u32(&sh->full[0], 0) : 0u;
-        const uint32_t afull0 = PAIR ? ptx::mapa_u32(&sh->afull, 0) : 0u;
+        const uint32_t afull0 = PAIR ? ptx::mapa_u32(&sh->afull[0], 0) : 0u;
         int stage = 0;
-        uint32_t phase = 0, a_phase = 0;
-        for (int p = wid; p < n_items; p += nworkers) {
+        uint32_t phase = 0;
+        int uc = 0;  // units taken by this CTA: query-tile buffer uc % NA, barrier parity (uc / NA) & 1
+        for (int p = wid; p < n_items; p += nworkers, uc++) {
             const Unit un = units[PAIR ? 2 * p + (int)rank : p];
             const int ntiles = (PAIR || un.a_rows > 0) ? (un.b_rows + BN - 1) / BN : 0;
-            // the unit's query tile, once
-            ptx::mbar_wait<64>(&sh->aempty, a_phase ^ 1);
+            const int ab = uc % NA;
+            const uint32_t a_par = (uint32_t)(uc / NA) & 1u;
+            uint8_t* smem_a = smem + (size_t)ab * ATB;
+            // the unit's query tile, once (A2: into the buffer the unit before last has released)
+            ptx::mbar_wait<64>(&sh->aempty[ab], a_par ^ 1);
             if (ptx::elect_one()) {
                 if (PAIR) {
-                    if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull, 2 * nkc * A_BYTES);
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&sh->afull[ab], 2 * nkc * A_BYTES);
                     for (int kc = 0; kc < nkc; kc++)
-                        ptx::tma_load_2d_cg2(smem + (size_t)kc * A_BYTES, &map_ah, afull0, kc * KE, un.a_row0);
+                        ptx::tma_load_2d_cg2(smem_a + (size_t)kc * A_BYTES, &map_ah, afull0 + (uint32_t)ab * 8, kc * KE, un.a_row0);
                 } else {
-                    ptx::mbar_arrive_expect_tx(&sh->afull, nkc * A_BYTES);
+                    ptx::mbar_arrive_expect_tx(&sh->afull[ab], nkc * A_BYTES);
                     for (int kc = 0; kc < nkc; kc++)
-                        ptx::tma_load_2d(smem + (size_t)kc * A_BYTES, &map_ah, &sh->afull, kc * KE, un.a_row0);
+                        ptx::tma_load_2d(smem_a + (size_t)kc * A_BYTES, &map_ah, &sh->afull[ab], kc * KE, un.a_row0);
                 }
             }
             __syncwarp();
-            a_phase ^= 1;
             for (int t = 0; t < ntiles; t++) {
                 const int brow = un.b_row0 + t * BN + (PAIR ? (int)rank * (BN / 2) : 0);
                 for (int kc = 0; kc < nkc; kc++) {
@@ -1202,16 +1349,18 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
             const uint32_t la0 = ptx::umma_desc_lo(ptx::smem_u32(smem));
             const uint32_t lb0 = ptx::umma_desc_lo(ptx::smem_u32(smem_b));
             int stage = 0;
-            uint32_t phase = 0, a_phase = 0;
+            uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             uint32_t mma_gt = 0;  // running tile index (trace builds)
-            for (int p = wid; p < n_items; p += nworkers) {
+            int uc = 0;
+            for (int p = wid; p < n_items; p += nworkers, uc++) {
                 const Unit un = units[PAIR ? 2 * p : p];
                 const int ntiles = (PAIR || un.a_rows > 0) ? (un.b_rows + BN - 1) / BN : 0;
-                ptx::mbar_wait(&sh->afull, a_phase);
+                const int ab = uc % NA;
+                const uint32_t la_u = la0 + (uint32_t)(ab * ATB) / 16;
+                ptx::mbar_wait(&sh->afull[ab], (uint32_t)(uc / NA) & 1u);
                 ptx::tcgen05_fence_after();
-                a_phase ^= 1;
                 for (int t = 0; t < ntiles; t++, mma_gt++) {
                     ptx::mbar_wait(&sh->tempty[acc], acc_phase ^ 1);
                     ptx::tcgen05_fence_after();
@@ -1220,7 +1369,7 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
                     for (int kc = 0; kc < nkc; kc++) {
                         ptx::mbar_wait(&sh->full[stage], phase);
                         ptx::tcgen05_fence_after();
-                        const uint32_t l_a = la0 + (uint32_t)(kc * A_BYTES) / 16;
+                        const uint32_t l_a = la_u + (uint32_t)(kc * A_BYTES) / 16;
                         const uint32_t l_b = lb0 + (uint32_t)(stage * BSB) / 16;
                         if (ptx::elect_one()) {
 #pragma unroll
@@ -1264,9 +1413,9 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
                 // query tile may be replaced once these MMAs retire
                 if (ptx::elect_one()) {
                     if (PAIR)
-                        ptx::umma_commit_cg2_mc(&sh->aempty, 3);
+                        ptx::umma_commit_cg2_mc(&sh->aempty[ab], 3);
                     else
-                        ptx::umma_commit(&sh->aempty);
+                        ptx::umma_commit(&sh->aempty[ab]);
                 }
                 __syncwarp();
             }
@@ -1275,8 +1424,8 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
         // ------------------------------------------------------------------ filter epilogue (every CTA)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale};
-        epilogue_run<L2, PAIR, true>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
+                   part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale, hot & 1, (hot & 2) ? 0 : 1};
+        epilogue_run<L2, PAIR, true, A2>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
     ptx::tcgen05_fence_before();
@@ -1302,14 +1451,20 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
         float *__restrict__ part_key, int *__restrict__ part_idx, int *__restrict__ part_cnt,                      \
         int *__restrict__ row_flags,                                                                               \
         float *__restrict__ cand_key_buf, int *__restrict__ cand_idx_buf, unsigned *__restrict__ gthr,             \
-        const float *__restrict__ a_row_scale, float b_scale, const int *__restrict__ row_map, int row_div
+        const float *__restrict__ a_row_scale, float b_scale, const int *__restrict__ row_map, int row_div, int hot
 #define NRB_TC3_ARGS                                                                                                  \
     map_ah, map_bh, units, n_units_p, nkc, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx, \
-        part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, a_row_scale, b_scale, row_map, row_div
+        part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, a_row_scale, b_scale, row_map, row_div, hot
 
 template <bool L2, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) topk_tc3_kernel(NRB_TC3_PARAMS) {
     tc3_body<L2, F16, true>(NRB_TC3_ARGS);
+}
+
+// fp16 CTA pairs with two resident query tiles (IVF list scan: short units)
+template <bool L2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) topk_tc3d_kernel(NRB_TC3_PARAMS) {
+    tc3_body<L2, true, true, true>(NRB_TC3_ARGS);
 }
 
 // single-CTA form (fp16 planes only)
@@ -1477,7 +1632,9 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* part_cnt, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
-                        int single, cudaStream_t st) {
+                        int single, int ivf_mode, cudaStream_t st) {
+    static const int no_one_shot = getenv("NRB_NO_ONE_SHOT") ? 2 : 0;  // A/B measurements only
+    const int hot = (ivf_mode == 2 ? 1 : 0) | no_one_shot;  // bit 0: hot rows (IVF phase B); bit 1: disable epi_single_tile
     NRB_REQUIRE(part_cnt, "tc1: part_cnt required (the filter kernels write unsorted partial rows)");
     NRB_REQUIRE(!single || f16, "tc1: the single-CTA form exists for the fp16 planes only");
     // what the KERNEL reads (the raw planes are the refine stage's business: *_eligible)
@@ -1514,20 +1671,34 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
         topk_tc3_kernel<L2V, F16V><<<grid, NUM_THREADS, v3_smem<F16V>(), st>>>(mah, mbh, units, n_units_dev, nkc, k, pw,      \
                                                                       margin_scale, a->norms, b->norms, a->n, b->n, \
                                                                       part_key, part_idx, part_cnt, row_flags, ck, ci, gthr,  \
-                                                                      ars, bsc, row_map, row_div);                  \
+                                                                      ars, bsc, row_map, row_div, hot);             \
     } while (0)
-    if (single) {
+    if (ivf_mode != 0 && f16 && !single) {
+        // IVF list scan: short units -> two resident query tiles
+        constexpr size_t SM2 = Tc3Lay<true, true, true>::SMEM;
+        if (metric == NRB_METRIC_L2) {
+            NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM2));
+            topk_tc3d_kernel<true><<<grid, NUM_THREADS, SM2, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
+                                                                   a->norms, b->norms, a->n, b->n, part_key, part_idx,
+                                                                   part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div, hot);
+        } else {
+            NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM2));
+            topk_tc3d_kernel<false><<<grid, NUM_THREADS, SM2, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
+                                                                    a->norms, b->norms, a->n, b->n, part_key, part_idx,
+                                                                    part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div, hot);
+        }
+    } else if (single) {
         constexpr size_t SM1 = Tc3Lay<true, false>::SMEM;
         if (metric == NRB_METRIC_L2) {
             NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM1));
             topk_tc3s_kernel<true><<<grid, NUM_THREADS, SM1, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
                                                                    a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                   part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
+                                                                   part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div, hot);
         } else {
             NRB_CUDA_CHECK(cudaFuncSetAttribute(topk_tc3s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM1));
             topk_tc3s_kernel<false><<<grid, NUM_THREADS, SM1, st>>>(mah, mbh, units, n_units_dev, nkc, k, pw, margin_scale,
                                                                     a->norms, b->norms, a->n, b->n, part_key, part_idx,
-                                                                    part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div);
+                                                                    part_cnt, row_flags, ck, ci, gthr, ars, bsc, row_map, row_div, hot);
         }
     } else if (metric == NRB_METRIC_L2) {
         if (f16)

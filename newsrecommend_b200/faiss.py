@@ -32,7 +32,7 @@ __all__ = [
 _FLT_MAX = 3.4028234663852886e38
 SMALL_NQ = 20  # faiss's distance_compute_blas_threshold: below it faiss itself leaves the GEMM route
 IVF_SMALL_NQ = 64  # IVF batches up to this size take the HBM-regime list scan (nrb_ivf_scan_small)
-IVF_QUERY_BATCH = 131072  # queries per nrb_ivf_search call (bounds the regrouped query planes and partial rows: ~8 GB at nprobe 16, k 50)
+IVF_QUERY_BATCH = 262144  # queries per nrb_ivf_search call (bounds the regrouped query planes and partial rows: ~16 GB at nprobe 16, k 50)
 
 
 # ------------------------------------------------------------------------------------ helpers

@@ -35,6 +35,55 @@ def load_article_table(path):
     return ids, emb
 
 
+def load_article_table_device(path, chunk_rows: int = 32768):
+    """news/article_table.npy straight into HBM: (article_ids i64[n], embeddings f32[n, d]) as CUDA
+    tensors, equal to load_article_table() bit for bit.
+
+    A float table (what Retrieval.py:6 can actually read: its np.load has no allow_pickle) never
+    becomes a numpy array: the .npy header is parsed, the float64 payload is read in chunks into two
+    page-locked staging buffers (file.readinto), each chunk goes host-to-device on a copy stream while
+    the next one is being read, and nrb_split_table_f64 does the casts of Retrieval.py:7-8 on the
+    device. An object-dtype table (what embedding_generate.py:124-131 writes) is pickled Python
+    floats; it has to go through the unpickler once, then takes the same device path."""
+    dev = nf._device()
+    with open(path, "rb") as f:
+        major, _ = np.lib.format.read_magic(f)
+        shape, fortran, dtype = (np.lib.format.read_array_header_1_0(f) if major == 1
+                                 else np.lib.format.read_array_header_2_0(f))
+        plain = not dtype.hasobject and dtype == np.float64 and not fortran and len(shape) == 2
+        if plain:
+            n, w = shape
+            table = torch.empty((n, w), dtype=torch.float64, device=dev)
+            stage = [torch.empty((chunk_rows, w), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            h2d, _ = nf._copy_streams()
+            h2d.wait_stream(torch.cuda.current_stream())
+            for c, r0 in enumerate(range(0, n, chunk_rows)):
+                r1 = min(n, r0 + chunk_rows)
+                buf = stage[c & 1]
+                if c >= 2:
+                    done[c & 1].synchronize()  # the copy that last used this staging buffer has finished
+                got = f.readinto(memoryview(buf.numpy()).cast("B")[: (r1 - r0) * w * 8])
+                if got != (r1 - r0) * w * 8:
+                    raise IOError("article table is truncated")
+                with torch.cuda.stream(h2d):
+                    table[r0:r1].copy_(buf[: r1 - r0], non_blocking=True)
+                    done[c & 1].record(h2d)
+            torch.cuda.current_stream().wait_stream(h2d)
+    if not plain:
+        arr = np.load(path, allow_pickle=True)
+        if arr.dtype == object:
+            arr = np.asarray(arr.tolist(), dtype=np.float64)
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.ndim == 2
+        n, w = arr.shape
+        table = torch.from_numpy(arr).to(dev)
+    ids = torch.empty(n, dtype=torch.int64, device=dev)
+    emb = torch.empty((n, w - 1), dtype=torch.float32, device=dev)
+    check(lib.nrb_split_table_f64(table.data_ptr(), n, w, emb.data_ptr(), ids.data_ptr(), nf._stream()), "split_table_f64")
+    return ids, emb
+
+
 def load_user_profiles(path):
     """news/test_user_profile.npy: pickled dict uid -> vector (Retrieval.py:28). Returns
     (uids i64[nu], profiles f32[nu, d]) in the dict's iteration order."""
@@ -64,20 +113,27 @@ def load_recommendations(path):
 
 
 # ---------------------------------------------------------------------------- the stage
-def retrieve_candidates(article_ids, embeddings, user_profiles, num_clusters=300, niter=80, verbose=False):
+def retrieve_candidates(article_ids, embeddings, user_profiles, num_clusters=300, niter=80, verbose=False,
+                        centroids=None):
     """Retrieval.py:11-34 batched. Returns a dict with
       offsets i64[nu+1], candidates i64[total]  -- CSR: user u's candidates (article ids)
-      user_list i64[nu], centroids f32[k, d], assignments i64[n], list_sizes i64[k]."""
+      user_list i64[nu], centroids f32[k, d], assignments i64[n], list_sizes i64[k].
+    centroids (optional, f32[k, d]): skip the k-means of lines 12-19 and use these (teacher-forced
+    comparison with another implementation of the stage)."""
     emb, _ = nf._to_device_f32(embeddings)
     users, _ = nf._to_device_f32(user_profiles)
     n, d = emb.shape
     ids = _dev(article_ids, torch.int64)
-    clustering = nf.Clustering(d, num_clusters)              # :12
-    clustering.niter = niter                                  # :13
-    clustering.verbose = verbose                              # :14
     index = nf.IndexHNSWFlat(d, 32)                           # :16 (exact L2, DESIGN section 1)
-    clustering.train(emb, index)                              # :18
-    centroids = nf.vector_float_to_array(clustering.centroids).reshape(num_clusters, d)  # :19
+    if centroids is None:
+        clustering = nf.Clustering(d, num_clusters)          # :12
+        clustering.niter = niter                              # :13
+        clustering.verbose = verbose                          # :14
+        clustering.train(emb, index)                          # :18
+        centroids = nf.vector_float_to_array(clustering.centroids).reshape(num_clusters, d)  # :19
+    else:
+        centroids = np.ascontiguousarray(centroids, dtype=np.float32).reshape(num_clusters, d)
+        index.add(centroids)
     _, assign = index.search(emb, 1)                          # :21
     assign = assign.reshape(-1)                               # :22
     # :23 -- the 300 boolean masks become one stable counting sort

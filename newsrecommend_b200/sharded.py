@@ -200,9 +200,11 @@ class ShardedIndexFlat:
         if self.exchange_mode == "allgather" or G == 1:
             D = torch.cat([p[0] for p in parts]) if len(parts) != 1 else parts[0][0]
             I = torch.cat([p[1] for p in parts]) if len(parts) != 1 else parts[0][1]
-            if gather or G == 1:
+            if gather:
                 return D, I
             spans = owned_rows(nq, G, self.rank, chunk)
+            if G == 1:
+                return D, I, spans
             sel = torch.cat([torch.arange(lo, hi) for lo, hi in spans]).to(D.device)
             return D[sel], I[sel], spans
         spans = owned_rows(nq, G, self.rank, chunk)

@@ -31,11 +31,11 @@ def test_kmeans_update_matches_sequential_fp32(nf, oracle):
     assert np.abs(c - ref64).max() <= np.abs(co - ref64).max() + 1e-7
 
 
-def test_build_lists_is_stable_counting_sort(nf):
+@pytest.mark.parametrize("n,nlist", [(50001, 300), (1_000_003, 250)])  # one-block scan / grouped scan (> 256 chunks)
+def test_build_lists_is_stable_counting_sort(nf, n, nlist):
     import torch
     from newsrecommend_b200._lib import check, lib
     rng = np.random.default_rng(1)
-    n, nlist = 50001, 300
     a = rng.integers(0, nlist, size=n)
     at = torch.from_numpy(a).cuda()
     off = torch.empty(nlist + 1, dtype=torch.int32, device="cuda")
@@ -112,6 +112,43 @@ def test_clustering_split_path_and_errors(nf):
         nf.Clustering(16, 4).train(bad, nf.IndexFlatL2(16))
 
 
+def _classify_ivf_mismatches(ivf_o, xq, nprobe, k, D, I, Do, Io, metric, gap=1e-5):
+    """Fails unless every query whose row differs from the oracle's is explained by a near-tie at
+    the coarse boundary: brute force (fp64) over each admissible probe set must reproduce the row."""
+    import itertools
+    off, ids, rows = ivf_o._build_csr()
+    cent = ivf_o.quantizer.xb.astype(np.float64)
+    explained = 0
+    for q in range(xq.shape[0]):
+        if compare_topk(D[q:q + 1], I[q:q + 1], Do[q:q + 1], Io[q:q + 1], metric)["ok"]:
+            continue
+        x = xq[q].astype(np.float64)
+        cs = cent @ x if metric == 0 else -((cent - x) ** 2).sum(1)  # larger is better
+        order = np.argsort(-cs, kind="stable")
+        kth, nxt = cs[order[nprobe - 1]], cs[order[nprobe]]
+        scale = max(abs(kth), (x * x).sum() if metric else 0.0, 1e-30)
+        assert abs(kth - nxt) <= gap * scale, ("no coarse near-tie explains query", q, kth, nxt)
+        lo = kth + gap * scale  # surely probed: better than the boundary by more than the gap
+        sure = [l for l in order if cs[l] > lo]
+        tie = [l for l in order if abs(cs[l] - kth) <= gap * scale]
+        ok = False
+        for pick in itertools.combinations(tie, nprobe - len(sure)):
+            lists = sure + list(pick)
+            sel = np.concatenate([np.arange(off[l], off[l + 1]) for l in lists])
+            xr = rows[sel].astype(np.float64)
+            sc = xr @ x if metric == 0 else ((xr - x) ** 2).sum(1)
+            o = np.argsort(-sc if metric == 0 else sc, kind="stable")[:k]
+            Dt = np.full((1, k), -3.4028235e38 if metric == 0 else 3.4028235e38)
+            It = np.full((1, k), -1, dtype=np.int64)
+            Dt[0, :len(o)], It[0, :len(o)] = sc[o], ids[sel][o]
+            if compare_topk(D[q:q + 1], I[q:q + 1], Dt, It, metric)["ok"]:
+                ok = True
+                break
+        assert ok, ("row matches no admissible probe set", q)
+        explained += 1
+    return explained
+
+
 def _same_centroids_ivf(nf, oracle, xb, nlist, metric, path):
     quant_o = oracle.IndexFlatIP(xb.shape[1]) if metric == 0 else oracle.IndexFlatL2(xb.shape[1])
     ivf_o = oracle.IndexIVFFlat(quant_o, xb.shape[1], nlist, metric)
@@ -142,8 +179,11 @@ def test_ivf_search_against_oracle(nf, oracle, metric, path):
         D, I = ivf_g.search(xq, 50)
         Do, Io = ivf_o.search(xq, 50)
         rep = compare_topk(D, I, Do, Io, metric)
-        # queries whose nprobe | nprobe+1 coarse gap is a near-tie may probe another list
-        assert rep["id_mismatch_queries"] <= 2 and rep["score_violations"] <= 100, rep
+        if not rep["ok"]:
+            # every disagreement must be a COARSE-boundary near-tie (the nprobe-th and (nprobe+1)-th
+            # centroid scores within 1e-5 relative, so a valid implementation may probe either list),
+            # and the GPU row must be the exact answer for one of the admissible probe sets
+            _classify_ivf_mismatches(ivf_o, xq, nprobe, 50, D, I, Do, Io, metric)
     # nprobe = nlist is an exact search (strongest IVF check)
     ivf_g.nprobe = 64
     D, I = ivf_g.search(xq, 50)

@@ -132,3 +132,75 @@ def test_finalize_cap_keeps_candidates_in_their_own_row_at_scale():
     assert np.unique(ccand).size == ccand.size
     tail = ccand[coff[nu - 1000]:] % 100
     assert np.unique(tail[tail != 99]).size > 40  # the last rows still draw from their whole lists
+
+
+def test_batched_stage_equals_the_oracle_teacher_forced(tmp_path, oracle):
+    """SURVEY 8f row 2 against the ORACLE (not against the shim): the oracle runs Retrieval.py:11-34
+    -- k-means (300 x 20 iterations), assign every article, lists, nearest centroid per user -- and
+    retrieve_candidates gets the oracle's centroids (teacher-forced): same assignments -> same CSR."""
+    from newsrecommend_b200 import pipeline
+    news, ids, x, users, gt = _synthetic_news(tmp_path, n=40000, nu=2000)
+    k, d = 300, x.shape[1]
+    clus = oracle.Clustering(d, k)
+    clus.niter = 20
+    index = oracle.IndexHNSWFlat(d, 32)
+    clus.train(x, index)                                              # :12-18
+    cent = oracle.vector_float_to_array(clus.centroids).reshape(k, d)  # :19
+    _, a = index.search(x, 1)                                         # :21
+    a = a.flatten()
+    cluster_to_articles = {i: ids[a == i] for i in range(k)}          # :23
+    ci = oracle.IndexFlatL2(d)
+    ci.add(cent)                                                      # :25-26
+    _, I = ci.search(users, 1)                                        # :30-32 (batched; nq >= 20 -> BLAS path)
+    out = pipeline.retrieve_candidates(ids, x, users, num_clusters=k, centroids=cent)
+    off, cand = out["offsets"].cpu().numpy(), out["candidates"].cpu().numpy()
+    ga, gl = out["assignments"].cpu().numpy(), out["user_list"].cpu().numpy()
+    # assignments / user lists may differ only where two centroids are at (near-)equal distance
+    for got, want, pts in ((ga, a, x), (gl, I[:, 0], users)):
+        for i in np.nonzero(got != want)[0]:
+            d1 = ((pts[i].astype(np.float64) - cent[got[i]]) ** 2).sum()
+            d2 = ((pts[i].astype(np.float64) - cent[want[i]]) ** 2).sum()
+            assert abs(d1 - d2) <= 1e-5 * max(d1, d2), (i, d1, d2)
+    same_assign = np.array_equal(ga, a)
+    n_same = 0
+    for u in range(len(users)):
+        ref = cluster_to_articles[int(I[u, 0])]                       # :33
+        if same_assign and gl[u] == I[u, 0]:
+            assert np.array_equal(cand[off[u]:off[u + 1]], ref)
+            n_same += 1
+    assert n_same >= 0.99 * len(users)
+
+
+def test_article_table_device_loader_both_formats(tmp_path):
+    """file -> page-locked staging -> HBM (no numpy array in between) for the float
+    table Retrieval.py:6 can read, and the object-dtype table embedding_generate.py:124-131 writes
+    (pickled Python floats: one pass through the unpickler, then the same device path). Both equal
+    the host loader bit for bit."""
+    from newsrecommend_b200 import pipeline
+    rng = np.random.default_rng(0)
+    n, d = 70_001, 250  # more than two staging chunks, ragged tail
+    x = rng.standard_normal((n, d))
+    ids = rng.permutation(10_000_000)[:n].astype(np.float64)
+    table = np.concatenate([x, ids[:, None]], axis=1)
+    np.save(tmp_path / "article_table.npy", table)
+    ids_h, emb_h = pipeline.load_article_table(tmp_path / "article_table.npy")
+    ids_d, emb_d = pipeline.load_article_table_device(tmp_path / "article_table.npy")
+    assert ids_d.is_cuda and emb_d.is_cuda and emb_d.dtype.is_floating_point and emb_d.is_contiguous()
+    assert np.array_equal(ids_d.cpu().numpy(), ids_h) and np.array_equal(emb_d.cpu().numpy(), emb_h)
+    assert np.array_equal(ids_h, ids.astype(np.int64)) and np.array_equal(emb_h, x.astype(np.float32))
+    # the producer's format: dtype=object rows of Python floats (needs allow_pickle)
+    small = table[:3_000]
+    obj = np.empty(small.shape, dtype=object)
+    obj[...] = small
+    np.save(tmp_path / "article_table_obj.npy", obj, allow_pickle=True)
+    with pytest.raises(ValueError):
+        np.load(tmp_path / "article_table_obj.npy")  # what Retrieval.py:6 would hit on the producer's file
+    ids_o, emb_o = pipeline.load_article_table(tmp_path / "article_table_obj.npy")
+    ids_od, emb_od = pipeline.load_article_table_device(tmp_path / "article_table_obj.npy")
+    assert np.array_equal(ids_o, ids_h[:3_000]) and np.array_equal(emb_o, emb_h[:3_000])
+    assert np.array_equal(ids_od.cpu().numpy(), ids_o) and np.array_equal(emb_od.cpu().numpy(), emb_o)
+    # float32 tables and Fortran order fall back to the generic route and still agree
+    np.save(tmp_path / "t32.npy", table[:500].astype(np.float32))
+    i32, e32 = pipeline.load_article_table_device(tmp_path / "t32.npy")
+    ih, eh = pipeline.load_article_table(tmp_path / "t32.npy")
+    assert np.array_equal(i32.cpu().numpy(), ih) and np.array_equal(e32.cpu().numpy(), eh)

@@ -202,3 +202,99 @@ def test_comparator_rejects_wrong_ids():
     assert compare_topk(Dt, np.array([[1, 3, 2]]), Dt, I, 0)["ok"]
     # score off by more than 1e-4 relative
     assert not compare_topk(D * (1 + 3e-4), I, D, I, 0)["ok"]
+
+
+# ------------------------------------------------------------------------------------------------
+# Independent cross-checks of the ORACLE itself. faiss is not installable in this image,
+# so the restatement is pinned from several independent sides instead: torch CPU (MKL sgemm + topk),
+# scikit-learn's brute-force neighbours and Lloyd step, numpy's own MT19937, and a vectorised fp64
+# re-derivation of the IVF semantics -- all on the committed golden fixtures.
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_golden_flat_against_torch_mkl_and_sklearn(metric):
+    import torch
+    from newsrecommend_b200.parity import compare_topk
+    g = np.load(os.path.join(GOLD, "flat_small.npz"))
+    xb, xq = torch.from_numpy(g["xb"]), torch.from_numpy(g["xq"])
+    ip = xq @ xb.T  # MKL sgemm: a different BLAS from the OpenBLAS behind the oracle's numpy blocks
+    if metric == 0:
+        D, I = torch.topk(ip, 10, dim=1, largest=True, sorted=True)
+    else:
+        d2 = (xq * xq).sum(1, keepdim=True) + (xb * xb).sum(1)[None, :] - 2 * ip
+        D, I = torch.topk(d2.clamp_min(0), 10, dim=1, largest=False, sorted=True)
+    rep = compare_topk(D.numpy(), I.numpy(), g[f"D{metric}"], g[f"I{metric}"], metric)
+    assert rep["ok"], rep
+    # fp64 brute force (ordered by (score, id)): the fixture's truth arrays
+    rep = compare_topk(g[f"D{metric}"], g[f"I{metric}"], g[f"Dt{metric}"], g[f"It{metric}"], metric)
+    assert rep["ok"], rep
+    if metric == 1:
+        from sklearn.neighbors import NearestNeighbors
+        nn = NearestNeighbors(n_neighbors=10, algorithm="brute", metric="euclidean").fit(g["xb"].astype(np.float64))
+        dist, idx = nn.kneighbors(g["xq"].astype(np.float64))
+        rep = compare_topk(dist ** 2, idx, g["D1"], g["I1"], 1)  # faiss L2 is the SQUARED distance
+        assert rep["ok"], rep
+
+
+def test_rand_perm_against_numpy_mt19937(oracle):
+    """std::mt19937(seed) raw outputs == numpy's MT19937 with legacy (init_genrand) seeding; the
+    oracle's rand_perm (faiss utils/random.cpp) restated on top of numpy's generator."""
+    for n, seed in [(20, 1234), (1000, 1235), (64000, 1234)]:
+        bg = np.random.MT19937()
+        bg._legacy_seeding(seed)
+        raw = bg.random_raw(n)  # 32-bit outputs
+        perm = np.arange(n, dtype=np.int64)
+        for i in range(n - 1):
+            j = i + int(raw[i]) % (n - i)
+            perm[i], perm[j] = perm[j], perm[i]
+        assert np.array_equal(oracle.rand_perm(n, seed), perm)
+    assert np.array_equal(np.load(os.path.join(GOLD, "rand_perm.npz"))["perm20_seed1234"], oracle.rand_perm(20, 1234))
+
+
+def test_golden_kmeans_iteration_against_sklearn_lloyd():
+    """One teacher-forced Lloyd iteration of the golden k-means trace reproduced by scikit-learn
+    (init = the recorded input centroids, max_iter = 1): same assignment, same means."""
+    from sklearn.cluster import KMeans
+    g = np.load(os.path.join(GOLD, "kmeans_small.npz"))
+    xs = g["xs"].astype(np.float64)
+    for it in range(g["cin"].shape[0]):
+        cin = g["cin"][it].astype(np.float64)
+        # assignment by fp64 brute force
+        d2 = (xs * xs).sum(1)[:, None] + (cin * cin).sum(1)[None, :] - 2 * xs @ cin.T
+        a = d2.argmin(1)
+        diff = np.nonzero(a != g["assign"][it])[0]
+        for i in diff:  # any disagreement with the fp32 oracle must be a near-tie
+            assert abs(d2[i, a[i]] - d2[i, g["assign"][it][i]]) <= 1e-5 * d2[i, a[i]]
+        km = KMeans(n_clusters=cin.shape[0], init=cin, n_init=1, max_iter=1, algorithm="lloyd", tol=0.0).fit(xs)
+        sizes = np.bincount(g["assign"][it], minlength=cin.shape[0])
+        keep = sizes > 0  # (empty clusters: faiss splits, scikit-learn relocates)
+        if diff.size == 0:
+            assert np.allclose(km.cluster_centers_[keep], g["cout"][it][keep], rtol=2e-5, atol=2e-6)
+        means = np.stack([xs[g["assign"][it] == c].mean(0) if sizes[c] else np.zeros(xs.shape[1]) for c in range(cin.shape[0])])
+        assert np.allclose(means[keep], g["cout"][it][keep], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_golden_ivf_against_fp64_rederivation(metric):
+    """IndexIVFFlat semantics re-derived in vectorised fp64 numpy from the fixture's centroids:
+    items go to their nearest centroid, a query scans the nprobe = 4 best lists, top-10 by score."""
+    from newsrecommend_b200.parity import compare_topk
+    g = np.load(os.path.join(GOLD, "ivf_small.npz"))
+    xb, xq, cent = g["xb"].astype(np.float64), g["xq"].astype(np.float64), g[f"cent{metric}"].astype(np.float64)
+
+    def coarse(x):  # larger is better
+        return x @ cent.T if metric == 0 else -((x * x).sum(1)[:, None] + (cent * cent).sum(1)[None, :] - 2 * x @ cent.T)
+
+    item_list = coarse(xb).argmax(1)
+    assert np.array_equal(np.bincount(item_list, minlength=cent.shape[0]), g[f"sizes{metric}"])
+    probe = np.argsort(-coarse(xq), axis=1, kind="stable")[:, :4]
+    D = np.empty((xq.shape[0], 10))
+    I = np.empty((xq.shape[0], 10), dtype=np.int64)
+    for q in range(xq.shape[0]):
+        sel = np.nonzero(np.isin(item_list, probe[q]))[0]
+        sc = xb[sel] @ xq[q] if metric == 0 else ((xb[sel] - xq[q]) ** 2).sum(1)
+        o = np.argsort(-sc if metric == 0 else sc, kind="stable")[:10]
+        D[q], I[q] = sc[o], sel[o]
+    rep = compare_topk(g[f"D{metric}"], g[f"I{metric}"], D, I, metric)
+    assert rep["ok"], rep
