@@ -143,6 +143,16 @@ size_t nrb_kmeans_update_workspace(int64_t n, int32_t k, int32_t kp);
 int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32_t kp,
                       const int64_t* assign, int32_t k, float* centroids, float* hassign,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* Data-parallel form of K1b (shared coarse quantizer, one all-reduce of <= 0.65 MB per
+ * Lloyd iteration; no reference analogue, the reference trains in one process at Retrieval.py:18).
+ * nrb_kmeans_partial_sums: the same segmented fp64 reduction over THIS rank's rows, but it stops
+ * before the division: sums f64[k, d + 1], columns 0..d-1 = sum of the assigned rows, column d =
+ * their count. The ranks add their tables (ncclAllReduce, fp64) and nrb_kmeans_means turns the
+ * total into centroids f32[k, d] = float(sum) * (1.0f / count) and hassign f32[k] = count -- the
+ * rounding of nrb_kmeans_update. Workspace: nrb_kmeans_update_workspace. */
+int nrb_kmeans_partial_sums(const float* x_raw, int64_t n, int32_t d, int32_t kp, const int64_t* assign,
+                            int32_t k, double* sums, void* workspace, size_t workspace_bytes, void* stream);
+int nrb_kmeans_means(const double* sums, int32_t k, int32_t d, float* centroids, float* hassign, void* stream);
 /* Host-side pieces of Clustering::train that faiss also runs on the host (tiny, sequential,
  * RNG-driven): rand_perm (utils/random.cpp, std::mt19937, seed 1234 subsample / seed+1 init)
  * and split_clusters (EPS = 1/1024, rng(1234)). Return value of split = nsplit. These two

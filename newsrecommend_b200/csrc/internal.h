@@ -96,7 +96,7 @@ size_t kmeans_update_ws(int64_t n, int k, int kp);
 // k-means objective sum over rows of |x - c|^2 (L2) or x.c (IP), exact fp32 products, fixed-order fp64 sum
 int launch_kmeans_update(const float* x_raw, int64_t n, int d, int kp, const int64_t* assign, int k, float* centroids,
                          float* hassign, void* workspace, const float* cent_in, int metric, double* obj_out,
-                         cudaStream_t st);
+                         cudaStream_t st, double* sums_out = nullptr);
 int launch_km_split(int d, int k, int64_t n, float* hassign, float* centroids, double* stats, cudaStream_t st);
 
 // small_batch.cu: exact fp32 recompute of the rows listed in list[0 .. *count) for k = 1 (device-driven)

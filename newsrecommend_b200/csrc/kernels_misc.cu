@@ -394,16 +394,20 @@ __global__ void km_partial_kernel(const float* __restrict__ x_raw, int kp, const
 __global__ void km_finish_kernel(const double* __restrict__ partial, const int* __restrict__ chunk_base,
                                  const int* __restrict__ offsets, int kp, int d, int k, float* __restrict__ centroids,
                                  float* __restrict__ hassign, const double* __restrict__ obj_part,
-                                 double* __restrict__ obj_out) {
+                                 double* __restrict__ obj_out, double* __restrict__ sums_out) {
     const int c = blockIdx.x;
     const int j0 = chunk_base[c], j1 = chunk_base[c + 1];
     const int cnt = offsets[c + 1] - offsets[c];
-    if (threadIdx.x == 0) hassign[c] = (float)cnt;
+    if (threadIdx.x == 0) {
+        if (sums_out) sums_out[(int64_t)c * (d + 1) + d] = (double)cnt;  // data-parallel form: [k, d + 1] sums | count
+        else hassign[c] = (float)cnt;
+    }
     for (int col = threadIdx.x; col < d; col += blockDim.x) {
         double s = 0;
 #pragma unroll 8
         for (int j = j0; j < j1; j++) s += partial[(int64_t)j * kp + col];
-        centroids[(int64_t)c * d + col] = cnt > 0 ? (float)s * (1.0f / (float)cnt) : 0.f;
+        if (sums_out) sums_out[(int64_t)c * (d + 1) + col] = s;
+        else centroids[(int64_t)c * d + col] = cnt > 0 ? (float)s * (1.0f / (float)cnt) : 0.f;
     }
     if (obj_out && c == 0) {  // objective = sum of the chunk objectives, fixed order
         __shared__ double red[256];
@@ -418,6 +422,19 @@ __global__ void km_finish_kernel(const double* __restrict__ partial, const int* 
         }
         if (threadIdx.x == 0) *obj_out = red[0];
     }
+}
+
+// Data-parallel k-means: centroids from the all-reduced [k, d + 1] table of fp64 sums | counts
+// (nrb_kmeans_partial_sums on every rank's rows, summed over the ranks): the same rounding as
+// km_finish_kernel -- float(sum) * (1.0f / count).
+__global__ void km_means_kernel(const double* __restrict__ sums, int k, int d, float* __restrict__ centroids,
+                                float* __restrict__ hassign) {
+    const int c = blockIdx.x;
+    const double* row = sums + (int64_t)c * (d + 1);
+    const float cnt = (float)row[d];
+    if (threadIdx.x == 0) hassign[c] = cnt;
+    for (int col = threadIdx.x; col < d; col += blockDim.x)
+        centroids[(int64_t)c * d + col] = cnt > 0.f ? (float)row[col] * (1.0f / cnt) : 0.f;
 }
 
 // faiss Clustering.cpp split_clusters on the device (same arithmetic as nrb_split_clusters_host
@@ -1273,7 +1290,7 @@ size_t kmeans_update_ws(int64_t n, int k, int kp) { return carve_km_update(nullp
 // centroids f32[k, d], hassign f32[k] from assign i64[n] (K1b): counting sort + plan + partial + finish
 int launch_kmeans_update(const float* x_raw, int64_t n, int d, int kp, const int64_t* assign, int k, float* centroids,
                          float* hassign, void* workspace, const float* cent_in, int metric, double* obj_out,
-                         cudaStream_t st) {
+                         cudaStream_t st, double* sums_out) {
     const KmUpdateWs u = carve_km_update(workspace, n, k, kp);
     int rc = launch_counting_sort_i64(assign, n, k, u.offsets, u.order, nullptr, u.cs, u.cs_bytes, st);
     if (rc) return rc;
@@ -1292,7 +1309,13 @@ int launch_kmeans_update(const float* x_raw, int64_t n, int d, int kp, const int
                                                       obj ? u.obj_part : nullptr);
     NRB_LAUNCH_CHECK();
     km_finish_kernel<<<k, 256, 0, st>>>(u.partial, u.chunk_base, u.offsets, kp, d, k, centroids, hassign,
-                                        obj ? u.obj_part : nullptr, obj ? obj_out : nullptr);
+                                        obj ? u.obj_part : nullptr, obj ? obj_out : nullptr, sums_out);
+    NRB_LAUNCH_CHECK();
+    return NRB_OK;
+}
+
+int launch_km_means(const double* sums, int k, int d, float* centroids, float* hassign, cudaStream_t st) {
+    km_means_kernel<<<k, 256, 0, st>>>(sums, k, d, centroids, hassign);
     NRB_LAUNCH_CHECK();
     return NRB_OK;
 }
@@ -1321,6 +1344,25 @@ extern "C" int nrb_kmeans_update(const float* x_raw, int64_t n, int32_t d, int32
     }
     return nrb::launch_kmeans_update(x_raw, n, d, kp, assign, k, centroids, hassign, workspace, nullptr, 0, nullptr,
                                      (cudaStream_t)stream);
+}
+
+extern "C" int nrb_kmeans_partial_sums(const float* x_raw, int64_t n, int32_t d, int32_t kp, const int64_t* assign,
+                                       int32_t k, double* sums, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    NRB_REQUIRE(n >= 0 && n < (1LL << 31) && k > 0 && d > 0 && kp >= d && kp % 32 == 0 && kp <= 2048 && sums,
+                "kmeans_partial_sums: bad arguments n=%lld k=%d d=%d kp=%d", (long long)n, k, d, kp);
+    if (workspace_bytes < nrb_kmeans_update_workspace(n, k, kp)) {
+        set_error("kmeans_partial_sums: workspace too small");
+        return NRB_ERR_WORKSPACE;
+    }
+    return nrb::launch_kmeans_update(x_raw, n, d, kp, assign, k, nullptr, nullptr, workspace, nullptr, 0, nullptr,
+                                     (cudaStream_t)stream, sums);
+}
+
+extern "C" int nrb_kmeans_means(const double* sums, int32_t k, int32_t d, float* centroids, float* hassign,
+                                void* stream) {
+    NRB_REQUIRE(sums && centroids && hassign && k > 0 && d > 0, "kmeans_means: bad arguments");
+    return nrb::launch_km_means(sums, k, d, centroids, hassign, (cudaStream_t)stream);
 }
 
 extern "C" int nrb_split_clusters(int32_t d, int32_t k, int64_t n, float* hassign, float* centroids, double* stats3,

@@ -1,7 +1,8 @@
 """Worker of tests/test_gpu_sharded.py::test_sharded_nccl_torchrun (launched with torchrun, one
 rank per GPU, NCCL): the catalog-sharded search must equal the single-GPU index and the oracle
 on the same inputs -- both exchange forms, gathered and per-rank results, and the host-array
-entry point. Prints SHARDED_NCCL_OK on rank 0."""
+entry point; then the sharded IVF index (shared quantizer, both training modes). Prints
+SHARDED_NCCL_OK on rank 0."""
 import os
 import sys
 
@@ -56,10 +57,61 @@ def main():
                 assert np.array_equal(D_pin[rows], D.cpu().numpy()[rows])
                 other = np.setdiff1d(np.arange(nq), rows)
                 assert (I_pin[other] == -7).all()  # rows owned by other ranks are not touched
+    ivf_checks(rank, world, nf, fo, compare_topk)
     dist.barrier()
     if rank == 0:
         print("SHARDED_NCCL_OK world=%d" % world)
     dist.destroy_process_group()
+
+
+def ivf_checks(rank, world, nf, fo, compare_topk):
+    """ShardedIndexIVFFlat (shared quantizer, row-sharding within lists) against the single-GPU
+    IndexIVFFlat and the oracle's IVF with the same centroids; both training modes."""
+    from newsrecommend_b200 import synth
+    from newsrecommend_b200.sharded import ShardedIndexIVFFlat, shard_range
+    nb, d, nq, k, nlist = 40_003, 250, 2_001, 50, 32
+    xb, topics = synth.g_skew(nb, d, 7, return_topics=True)
+    xq = synth.user_profiles(xb, topics, nq, 8)
+    xb_dev, xq_dev = torch.from_numpy(xb).cuda(), torch.from_numpy(xq).cuda()
+    lo, hi = shard_range(nb, world, rank)
+    for metric in (0, 1):
+        single = nf.IndexIVFFlat(nf.IndexFlat(d, metric), d, nlist, metric)
+        single.train(xb_dev)
+        single.add(xb_dev)
+        for mode in ("gather", "data_parallel"):
+            idx = ShardedIndexIVFFlat(d, nlist, metric, chunk_queries=1024)
+            idx.train_local(xb_dev[lo:hi], lo, nb, mode=mode)
+            cent = idx.quantizer.reconstruct_n()
+            if mode == "gather":  # same subsample, same deterministic trainer: bit-equal centroids
+                assert np.array_equal(cent, single.quantizer.reconstruct_n()), (metric, "gather centroids differ")
+            else:
+                o1, o2 = idx.iteration_stats[-1].obj, single.clustering.iteration_stats[-1].obj
+                assert abs(o1 - o2) <= 0.02 * abs(o2), (metric, o1, o2)
+            t = torch.from_numpy(cent).cuda()
+            dist.broadcast(t, src=0)
+            assert np.array_equal(t.cpu().numpy(), cent), "ranks hold different centroids"
+            idx.add_local(xb_dev[lo:hi], lo, nb)
+            sizes = torch.from_numpy(idx.local.list_sizes().astype(np.int64)).cuda()
+            dist.all_reduce(sizes)
+            # oracle IVF with THESE centroids (teacher-forced)
+            qo = fo.IndexFlat(d, metric)
+            qo.add(cent)
+            ref = fo.IndexIVFFlat(qo, d, nlist, metric)
+            ref.train(xb)
+            ref.add(xb)
+            assert np.array_equal(sizes.cpu().numpy(), ref.list_sizes()), "list sizes do not add up"
+            for nprobe in (1, 8):
+                idx.nprobe = ref.nprobe = single.nprobe = nprobe
+                D, I = idx.search(xq_dev, k)
+                Do, Io = ref.search(xq, k)
+                rep = compare_topk(D.cpu().numpy(), I.cpu().numpy(), Do, Io, metric)
+                assert rep["ok"], (metric, mode, nprobe, rep)
+                if mode == "gather":
+                    Ds, Is = single.search(xq_dev, k)
+                    assert compare_topk(D.cpu().numpy(), I.cpu().numpy(), Ds.cpu().numpy(), Is.cpu().numpy(), metric)["ok"]
+                Dr, Ir, spans = idx.search(xq_dev, k, gather=False)
+                rows = np.concatenate([np.arange(a, b) for a, b in spans])
+                assert torch.equal(Ir, I[torch.from_numpy(rows).cuda()])
 
 
 if __name__ == "__main__":

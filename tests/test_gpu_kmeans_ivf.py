@@ -357,3 +357,40 @@ def test_fused_trainer_equals_stepwise_trainer(nf, metric):
             check(lib.nrb_split_clusters_host(250, k, x.shape[0], hh.ctypes.data, ch.ctypes.data))
             cent = torch.from_numpy(ch).cuda()
     assert np.array_equal(cent.cpu().numpy().reshape(-1), outs[0][0])
+
+
+def test_kmeans_partial_sums_and_means_equal_update(nf):
+    """Data-parallel pieces (nrb_kmeans_partial_sums + nrb_kmeans_means) on one rank: bit-equal to
+    nrb_kmeans_update; and the sum of two half-tables gives the same centroids to 1 ulp."""
+    import torch
+    from newsrecommend_b200._lib import check, lib
+    rng = np.random.default_rng(11)
+    n, d, k = 20_000, 250, 37
+    x = torch.from_numpy(rng.standard_normal((n, d), dtype=np.float32)).cuda()
+    assign = torch.from_numpy(rng.integers(0, k - 1, n)).cuda()  # cluster k-1 stays empty
+    xs = nf.PackedMatrix.from_tensor(x, planes=("raw",))
+    cent0, h0 = nf.kmeans_update(xs, assign, k)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def table(lo, hi):
+        t = torch.zeros(k * (d + 1), dtype=torch.float64, device="cuda")
+        part = nf.PackedMatrix.from_tensor(x[lo:hi], planes=("raw",))
+        wsb = lib.nrb_kmeans_update_workspace(hi - lo, k, part.kp)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        a = assign[lo:hi].contiguous()
+        check(lib.nrb_kmeans_partial_sums(part.raw.data_ptr(), hi - lo, d, part.kp, a.data_ptr(), k, t.data_ptr(),
+                                          ws.data_ptr(), wsb, st), "partial_sums")
+        return t
+
+    def means(t):
+        cent = torch.empty((k, d), dtype=torch.float32, device="cuda")
+        h = torch.empty(k, dtype=torch.float32, device="cuda")
+        check(lib.nrb_kmeans_means(t.data_ptr(), k, d, cent.data_ptr(), h.data_ptr(), st), "means")
+        return cent, h
+
+    c1, h1 = means(table(0, n))
+    assert torch.equal(c1, cent0) and torch.equal(h1, h0)
+    assert float(h1[k - 1]) == 0.0 and float(c1[k - 1].abs().max()) == 0.0
+    c2, h2 = means(table(0, 7_777) + table(7_777, n))
+    assert torch.equal(h2, h0)
+    assert torch.allclose(c2, cent0, rtol=3e-7, atol=1e-9)
