@@ -120,6 +120,20 @@ int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, in
                     int64_t id_base, float* D, int64_t* I, void* workspace,
                     size_t workspace_bytes, int32_t path, void* stream);
 
+/* nrb_search_flat with per-query bounds the caller already knows: seed_kth f32[nq] (device) holds,
+ * in D's domain (a score for IP, a squared distance for L2), a value that at least k items of the
+ * WHOLE catalog the caller is searching reach -- e.g. the k-th best over a row sample, or over
+ * another shard. The kernel's shared running bounds start there instead of at -inf, so every unit
+ * skips the append-heavy warm-up of its first tiles; +-FLT_MAX / NaN = no bound for that query.
+ * Results: every item of b that scores at least the bound is found exactly as nrb_search_flat finds
+ * it; a query may come back with fewer than k results from THIS matrix (the rest padded with -1)
+ * when the bound came from elsewhere -- the k-way merge over the shards restores the global top-k
+ * (sharded.py). Honoured by the filter paths (their margin absorbs the estimate error of the bounding
+ * item); the 3xTF32 paths ignore it. No reference analogue: faiss keeps one heap per query. */
+int nrb_search_flat_seeded(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
+                           int64_t id_base, float* D, int64_t* I, void* workspace,
+                           size_t workspace_bytes, int32_t path, const float* seed_kth, void* stream);
+
 /* Queries that NRB_PATH_TC1 had to recompute with the 3xTF32 kernel since the library was loaded
  * (candidate slots exhausted inside the error margin, or an estimate outside its bound). */
 int64_t nrb_fallback_query_count(void);

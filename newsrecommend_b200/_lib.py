@@ -24,7 +24,7 @@ SYMBOLS = [
     "nrb_version", "nrb_last_error", "nrb_device_info", "nrb_launch_count",
     "nrb_profile_enable", "nrb_profile_read", "nrb_set_tc_variant",
     "nrb_pack_rows", "nrb_pack_rows_h16", "nrb_gather_rows", "nrb_gather_i64", "nrb_normalize_l2",
-    "nrb_search_flat_workspace", "nrb_search_flat", "nrb_fallback_query_count", "nrb_plan_flat_describe",
+    "nrb_search_flat_workspace", "nrb_search_flat", "nrb_search_flat_seeded", "nrb_fallback_query_count", "nrb_plan_flat_describe",
     "nrb_kmeans_update_workspace", "nrb_kmeans_update", "nrb_kmeans_partial_sums", "nrb_kmeans_means",
     "nrb_rand_perm_host", "nrb_split_clusters_host", "nrb_split_clusters",
     "nrb_kmeans_train_workspace", "nrb_kmeans_train",
@@ -69,6 +69,7 @@ lib.nrb_normalize_l2.argtypes = [_vp, _i64, _i32, _i64, _vp]
 lib.nrb_search_flat_workspace.restype = _sz
 lib.nrb_search_flat_workspace.argtypes = [_i64, _i64, _i32, _i32]
 lib.nrb_search_flat.argtypes = [_mp, _mp, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _i32, _vp]
+lib.nrb_search_flat_seeded.argtypes = [_mp, _mp, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _i32, _vp, _vp]
 lib.nrb_fallback_query_count.restype = _i64
 lib.nrb_plan_flat_describe.argtypes = [_i64, _i64, _i32, _i32, _vp]
 lib.nrb_kmeans_update_workspace.restype = _sz

@@ -549,9 +549,19 @@ extern "C" size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, i
 
 namespace nrb {
 
+// gthr[i] = ordered-uint key of seed[i] (a score for IP, a squared distance for L2): a lower bound of
+// query i's k-th best key that the caller already knows; +-FLT_MAX / non-finite = no bound.
+__global__ void seed_bounds_kernel(const float* __restrict__ seed, int64_t nq, int l2, unsigned* __restrict__ gthr) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = seed[i];
+        const bool ok = fabsf(v) < 3.0e38f;  // false for NaN, inf and the FLT_MAX padding of a short result row
+        gthr[i] = ok ? ordered_u32(l2 ? -v : v) : 0u;
+    }
+}
+
 static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric, int k, int64_t id_base,
                             float* D, int64_t* I, void* workspace, size_t workspace_bytes, int path,
-                            cudaStream_t st) {
+                            cudaStream_t st, const float* seed_kth = nullptr) {
     if (path == NRB_PATH_AUTO)
         path = tc16_eligible(q, b, k) ? NRB_PATH_TC16 : tc1_eligible(q, b, k) ? NRB_PATH_TC1 : NRB_PATH_TC;
     if (path == NRB_PATH_TC1 && !tc1_eligible(q, b, k)) {
@@ -579,7 +589,18 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         rc = launch_fill_flat_units(w.units, w.n_units, w.src, q->n, b->n, p.nqt, p.full_pairs, p.tail_pairs, p.tsplit,
                                     p.chunk_rows, p.wgs, st);
     if (rc) return rc;
-    if (w.gthr) NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
+    // Seeded bounds are honoured by the filter paths only: their margin absorbs the difference between
+    // the caller's exact score of the bounding item and this kernel's estimate of the same item; the
+    // 3xTF32 kernels compare with no margin and start cold.
+    const bool seeded = seed_kth && filt && w.gthr;
+    if (seeded) {
+        int64_t blocks = (q->n + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        seed_bounds_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed_kth, q->n, metric == NRB_METRIC_L2 ? 1 : 0, w.gthr);
+        NRB_LAUNCH_CHECK();
+    } else if (w.gthr) {
+        NRB_CUDA_CHECK(cudaMemsetAsync(w.gthr, 0, (size_t)q->n * sizeof(unsigned), st));
+    }
     if (!filt) {
         {
             ProfScope prof(st);
@@ -600,7 +621,8 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         ProfScope prof(st);
         rc = launch_topk_tc1_dev(q, b, w.units, w.n_units, p.grid, metric, k, pw, 2.f * eps_xmax, w.part_key,
                                  w.part_idx, w.part_cnt, w.flags, w.scratch, w.scratch_bytes, w.gthr, nullptr, 1,
-                                 path == NRB_PATH_TC16, p.single, (!p.single && b->n <= 256) ? 1 : 0, st);  // <= 256 items: every unit is one tile (coarse search, nearest centroid) -> the short-unit kernel
+                                 path == NRB_PATH_TC16, p.single, (!p.single && b->n <= 256) ? 1 : 0, st,
+                                 seeded ? 1 : 0);  // <= 256 items: every unit is one tile (coarse search, nearest centroid) -> the short-unit kernel
     }
     if (rc) return rc;
     if ((rc = launch_gather_refine(w.part_key, w.part_idx, w.part_cnt, w.src, p.S, q->n, k, pw, metric, q, b, eps_xmax,
@@ -670,6 +692,21 @@ extern "C" int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t
     int rc = require_device();
     if (rc) return rc;
     return search_flat_impl(q, b, metric, k, id_base, D, I, workspace, workspace_bytes, path, (cudaStream_t)stream);
+}
+
+extern "C" int nrb_search_flat_seeded(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
+                                      int64_t id_base, float* D, int64_t* I, void* workspace,
+                                      size_t workspace_bytes, int32_t path, const float* seed_kth, void* stream) {
+    NRB_REQUIRE(q && b && D && I, "search_flat_seeded: null argument");
+    NRB_REQUIRE(metric == NRB_METRIC_INNER_PRODUCT || metric == NRB_METRIC_L2, "search_flat_seeded: bad metric %d", metric);
+    NRB_REQUIRE(k >= 1 && k <= NRB_MAX_K, "search_flat_seeded: k=%d out of range [1,%d]", k, NRB_MAX_K);
+    NRB_REQUIRE(q->d == b->d && q->kp == b->kp, "search_flat_seeded: dimension mismatch");
+    NRB_REQUIRE(q->n >= 0 && b->n >= 0 && b->n < (1LL << 31) - 4096 && q->n < (1LL << 31), "search_flat_seeded: sizes out of range");
+    NRB_REQUIRE(path >= NRB_PATH_AUTO && path <= NRB_PATH_TC16, "search_flat_seeded: bad path %d", path);
+    if (q->n == 0) return NRB_OK;
+    int rc = require_device();
+    if (rc) return rc;
+    return search_flat_impl(q, b, metric, k, id_base, D, I, workspace, workspace_bytes, path, (cudaStream_t)stream, seed_kth);
 }
 
 extern "C" int64_t nrb_fallback_query_count(void) { return (int64_t)g_fallback_queries.load(); }

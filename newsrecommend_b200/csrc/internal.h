@@ -50,7 +50,7 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* part_cnt, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
-                        int single, int ivf_mode, cudaStream_t st);
+                        int single, int ivf_mode, cudaStream_t st, int seeded = 0);
 // ivf_mode: 0 = flat search; 1 = IVF list scan, cold rows (two resident query tiles: units are short);
 // 2 = IVF phase B, every row starts from its query's shared bound (also: no scheduled prunes in units
 // under 16 tiles, no union prune at the end of a unit)

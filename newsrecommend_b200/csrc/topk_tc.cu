@@ -105,19 +105,22 @@ __device__ long long g_trace[9][NRB_TRACE_TILES][4];
 // scheduled prunes of the same warps: [who][prune #][0 publish, 1 partner arrived, 2 rows done, 3 partner done]
 __device__ long long g_trace_prune[9][64][4];
 __device__ int g_trace_prune_n[9];
+// 1: the launch records (set per launch by the host side: NRB_TRACE_IVF_MODE=1 / 2 keeps only the
+// phase A / phase B launches of an IVF scan, so that the LAST launch does not overwrite the others)
+__device__ int g_trace_enable = 1;
 #define NRB_TRP(who, ev)                                                                                   \
     do {                                                                                                   \
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_prune_n[who] < 64)                        \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_enable && g_trace_prune_n[who] < 64)      \
             g_trace_prune[who][g_trace_prune_n[who]][ev] = clock64();                                      \
     } while (0)
-#define NRB_TRP_NEXT(who)                                                        \
-    do {                                                                         \
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_trace_prune_n[who]++; \
+#define NRB_TRP_NEXT(who)                                                                           \
+    do {                                                                                            \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_enable) g_trace_prune_n[who]++; \
     } while (0)
-#define NRB_TR(who, tile, ev)                                                                     \
-    do {                                                                                          \
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < (uint32_t)NRB_TRACE_TILES)      \
-            g_trace[who][tile][ev] = clock64();                                                   \
+#define NRB_TR(who, tile, ev)                                                                                      \
+    do {                                                                                                           \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_trace_enable && (tile) < (uint32_t)NRB_TRACE_TILES)      \
+            g_trace[who][tile][ev] = clock64();                                                                    \
     } while (0)
 #else
 #define NRB_TR(who, tile, ev) \
@@ -698,6 +701,8 @@ struct EpiArgs {
     // (rows over pw entries are tightened one by one; the in-tile overflow guard stays)
     int hot;
     int one_shot_ok;  // 1: one-tile units take epi_single_tile (0 only for A/B measurements: NRB_NO_ONE_SHOT)
+    int seeded;       // 1: the shared bounds were seeded by the caller (nrb_search_flat_seeded)
+    int first_shot_ok;  // 1: the first tile of a cold multi-tile unit takes single_tile_call (0: NRB_NO_FIRST_SHOT, A/B)
 };
 constexpr int HOT_MIN_TILES = 16;
 
@@ -747,6 +752,25 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
         // filter kernels, one-tile unit, cold rows: per-thread bisection in registers (epi_single_tile)
         const bool hot = IVFX && A.hot;
         const bool one_shot = IVFX && NEED_QN && !hot && ntiles == 1 && A.one_shot_ok;
+        // Cold multi-tile units (flat search: full-catalog and first-round tail units; IVF phase A): the
+        // generic path appends the whole first tile (every key beats -inf: 256 entries per row, 112k
+        // cycles) and then prunes 256 entries per row (58k). Their first tile takes the in-register
+        // bisection of single_tile_call instead: ~k + margin-set entries per row are appended, the row's
+        // threshold is known at once and the scheduled prune after tile 1 is skipped. The two warps of a
+        // lane quarter must take the same path (barriers inside): they agree through shared memory on
+        // whether ANY of their 32 rows already holds a bound from another unit of its query.
+        bool first_shot = false;
+        if (NEED_QN && !hot && ntiles > 1 && A.first_shot_ok && !A.seeded) {
+            unsigned g0 = 0u;
+            if (st.gslot) g0 = *(volatile unsigned*)st.gslot;
+            if (wg == 0)
+                xs->nthr[row] = g0 != 0u ? 1.f : 0.f;
+            else
+                xs->lb[row] = g0 != 0u ? 1u : 0u;
+            ptx::named_bar_sync(3 + quad, 64);
+            const bool warm = xs->nthr[row] != 0.f || xs->lb[row] != 0u;
+            first_shot = !__any_sync(0xffffffffu, warm);
+        }
         for (int t = 0; t < ntiles; t++, gt++) {
             const int acc = (int)(gt & 1);
             const uint32_t acc_phase = (gt >> 1) & 1;
@@ -780,12 +804,16 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                         ptx::mbar_arrive(&tempty[acc]);
                 }
             };
-            if (IVFX && one_shot) {
+            if ((IVFX && one_shot) || (first_shot && t == 0)) {
                 const OneShotOut o = single_tile_call<L2, PAIR>(taddr0, valid, un.b_row0 + col_base, nrm_t, st.sc, st.inv, st.qn,
                                                               st.margin, myk, myi, A.k, xs, wg, row, quad,
                                                               acc ? tempty_remote1 : tempty_remote0, &tempty[acc]);
-                st.cnt = o.cnt;
-                st.base = o.cnt;
+                st.cnt = live ? o.cnt : 0;
+                st.base = st.cnt;
+                if (first_shot && live && o.lb > NEG_INF) {  // the unit goes on: appends continue above the bound
+                    st.thr = fmaxf(st.thr, o.lb - st.margin);
+                    st.cthr = L2 ? st.thr : st.thr * st.sc;
+                }
                 NRB_TR(warp - EPI_WARP0 + 1, gt, 2);
                 if (wg == 0 && st.gslot && o.lb > NEG_INF) atomicMax(st.gslot, ordered_u32(o.lb));
             } else if (valid >= HALF_N) {
@@ -821,7 +849,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             // half) do it together on the union of their buffers: see union_tighten_rows.
             NRB_TR(warp - EPI_WARP0 + 1, gt, 3);
             const uint32_t tp = (uint32_t)t + 1u;
-            if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles && !(hot && ntiles < HOT_MIN_TILES)) {
+            if ((tp & (tp - 1u)) == 0u && t + 1 < ntiles && !(hot && ntiles < HOT_MIN_TILES) && !(first_shot && t == 0)) {
                 xs->cnt[wg][row] = st.cnt;
                 xs->fresh[wg][row] = st.cnt - st.base;
                 xs->thr[wg][row] = st.thr;
@@ -831,7 +859,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 NRB_TRP(warp - EPI_WARP0 + 1, 1);
                 union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
                                    A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw,
-                                   A.row_map ? max(4, A.k >> 2) : 0);
+                                   (A.row_map || A.seeded) ? max(4, A.k >> 2) : 0);
                 NRB_TRP(warp - EPI_WARP0 + 1, 2);
                 ptx::named_bar_sync(3 + quad, 64);
                 NRB_TRP(warp - EPI_WARP0 + 1, 3);
@@ -1010,7 +1038,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         // ------------------------------------------------------------------ selection epilogue
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0, 0, 0};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, 0);
     }
 
@@ -1150,7 +1178,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0};
+                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0, 0, 0};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
@@ -1424,7 +1452,7 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
         // ------------------------------------------------------------------ filter epilogue (every CTA)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale, hot & 1, (hot & 2) ? 0 : 1};
+                   part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale, hot & 1, (hot & 2) ? 0 : 1, (hot & 4) ? 1 : 0, (hot & 8) ? 0 : 1};
         epilogue_run<L2, PAIR, true, A2>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
@@ -1632,9 +1660,12 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
                         const int* n_units_dev, int grid, int metric, int k, int pw, float margin_scale,
                         float* part_key, int* part_idx, int* part_cnt, int* row_flags, void* scratch,
                         size_t scratch_bytes, unsigned* gthr, const int* row_map, int row_div, int f16,
-                        int single, int ivf_mode, cudaStream_t st) {
-    static const int no_one_shot = getenv("NRB_NO_ONE_SHOT") ? 2 : 0;  // A/B measurements only
-    const int hot = (ivf_mode == 2 ? 1 : 0) | no_one_shot;  // bit 0: hot rows (IVF phase B); bit 1: disable epi_single_tile
+                        int single, int ivf_mode, cudaStream_t st, int seeded) {
+    static const int no_one_shot = (getenv("NRB_NO_ONE_SHOT") ? 2 : 0) | (getenv("NRB_NO_FIRST_SHOT") ? 8 : 0);  // A/B measurements only
+    // bit 0: hot rows (IVF phase B); bit 1: disable epi_single_tile for one-tile units; bit 2: gthr was
+    // seeded by the caller (rows start from a known bound: scheduled prunes skip rows with few new
+    // candidates); bit 3: disable the in-register first tile of cold multi-tile units
+    const int hot = (ivf_mode == 2 ? 1 : 0) | no_one_shot | (seeded ? 4 : 0);
     NRB_REQUIRE(part_cnt, "tc1: part_cnt required (the filter kernels write unsorted partial rows)");
     NRB_REQUIRE(!single || f16, "tc1: the single-CTA form exists for the fp16 planes only");
     // what the KERNEL reads (the raw planes are the refine stage's business: *_eligible)
@@ -1650,6 +1681,13 @@ int launch_topk_tc1_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* un
         set_error("tc1: scratch too small");
         return NRB_ERR_WORKSPACE;
     }
+#ifdef NRB_TRACE
+    {
+        const char* e = getenv("NRB_TRACE_IVF_MODE");
+        const int en = (!e || atoi(e) == ivf_mode) ? 1 : 0;
+        NRB_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_trace_enable, &en, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    }
+#endif
     CUtensorMap mah, mbh;
     int rc;
     if (f16) {

@@ -230,18 +230,26 @@ class PackedMatrix:
 
 
 def _search_flat_dev(q: PackedMatrix, b: PackedMatrix, metric: int, k: int, id_base: int = 0,
-                     path: int = PATH_AUTO):
-    """nrb_search_flat on packed matrices -> (D f32[nq,k], I i64[nq,k]) CUDA tensors."""
-    nq = q.n
+                     path: int = PATH_AUTO, seed: torch.Tensor | None = None, rows: int | None = None,
+                     qrange: tuple[int, int] | None = None):
+    """nrb_search_flat on packed matrices -> (D f32[nq,k], I i64[nq,k]) CUDA tensors. seed f32[nq]:
+    per-query bounds for nrb_search_flat_seeded; rows: search only the first `rows` rows of b;
+    qrange = (row0, n): only these rows of q."""
+    q0, nq = qrange if qrange is not None else (0, q.n)
     D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     if nq == 0:
         return D, I
     wsb = lib.nrb_search_flat_workspace(nq, b.n, k, q.kp)
     ws = torch.empty(wsb, dtype=torch.uint8, device=q.device)
-    qs, bs = q.struct(), b.struct()
-    check(lib.nrb_search_flat(C.byref(qs), C.byref(bs), metric, k, id_base, D.data_ptr(), I.data_ptr(),
-                              ws.data_ptr(), wsb, path, _stream()), "search_flat")
+    qs, bs = q.struct(q0, nq), b.struct(0, rows)
+    if seed is not None:
+        assert seed.dtype == torch.float32 and seed.numel() == nq and seed.is_contiguous()
+        check(lib.nrb_search_flat_seeded(C.byref(qs), C.byref(bs), metric, k, id_base, D.data_ptr(), I.data_ptr(),
+                                         ws.data_ptr(), wsb, path, seed.data_ptr(), _stream()), "search_flat_seeded")
+    else:
+        check(lib.nrb_search_flat(C.byref(qs), C.byref(bs), metric, k, id_base, D.data_ptr(), I.data_ptr(),
+                                  ws.data_ptr(), wsb, path, _stream()), "search_flat")
     return D, I
 
 
@@ -322,13 +330,17 @@ class IndexFlat:
             self._xb = PackedMatrix(self.d, planes=_INDEX_PLANES, track_max_norm=True)
         return self._xb
 
-    def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0):
+    def search_packed(self, q: PackedMatrix, k: int, id_base: int = 0, seed=None, rows: int | None = None,
+                      qrange: tuple[int, int] | None = None):
+        """seed / rows / qrange: see _search_flat_dev (bounds known to the caller; a row prefix as the
+        sample; a slice of the packed query batch)."""
         if self.ntotal == 0:
             # faiss on an empty index: I = -1, D = +/-FLT_MAX (also what an empty catalog shard returns)
-            D = torch.full((q.n, k), _FLT_MAX if self.metric_type == METRIC_L2 else -_FLT_MAX,
+            nq = qrange[1] if qrange is not None else q.n
+            D = torch.full((nq, k), _FLT_MAX if self.metric_type == METRIC_L2 else -_FLT_MAX,
                            dtype=torch.float32, device=q.device)
-            return D, torch.full((q.n, k), -1, dtype=torch.int64, device=q.device)
-        return _search_flat_dev(q, self._packed(), self.metric_type, k, id_base, self.path)
+            return D, torch.full((nq, k), -1, dtype=torch.int64, device=q.device)
+        return _search_flat_dev(q, self._packed(), self.metric_type, k, id_base, self.path, seed, rows, qrange)
 
     def search(self, x, k: int, D=None, I=None):
         """(D, I) = search(x, k). Like faiss, optional preallocated numpy outputs D f32[nq,k],

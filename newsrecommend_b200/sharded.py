@@ -21,11 +21,15 @@ the same code runs under gloo on CPU with the oracle index and numpy stand-ins (
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 CHUNK_WAVES = 7  # queries per chunk = CHUNK_WAVES full waves of the search kernel (7 x 18,944)
+# rows of the sample pass that seeds every shard's running bounds (0: off; NRB_SEED_ROWS overrides for A/B runs)
+SEED_SAMPLE_ROWS = int(os.environ.get("NRB_SEED_ROWS", "8192"))
 
 
 def shard_range(nb: int, world: int, rank: int) -> tuple[int, int]:
@@ -127,8 +131,9 @@ class _ShardedSearch:
         return 1 << 17
 
     # ------------------------------------------------------------------ search pieces
-    def search_local(self, xq, k: int):
-        """Per-shard top-k of a raw query chunk with GLOBAL ids: (D f32[n,k], I i64[n,k]) tensors."""
+    def search_local(self, xq, k: int, per: int | None = None):
+        """Per-shard top-k of a raw query chunk with GLOBAL ids: (D f32[n,k], I i64[n,k]) tensors.
+        per: rows of the chunk each rank owns in the exchange (rank r: [r*per, (r+1)*per))."""
         raise NotImplementedError
 
     def _exchange_start(self, P: torch.Tensor, per: int):
@@ -167,7 +172,7 @@ class _ShardedSearch:
             parts.append(self.codec.merge(recv, self._bases(), self.metric_type))
 
         for c0, c1, per in chunk_slices(nq, G, chunk):
-            D, I = self.search_local(xq[c0:c1], k)
+            D, I = self.search_local(xq[c0:c1], k, per)
             P = self.codec.pack(D, I, self.id_base)
             nxt = self._exchange_start(P, per)
             if pending is not None:
@@ -253,7 +258,7 @@ class _ShardedSearch:
                 dist.all_gather_into_tensor(full, mine, group=self.group)
             else:
                 full = mine
-            D, I = self.search_local(full[: c1 - c0], k)
+            D, I = self.search_local(full[: c1 - c0], k, per)
             P = self.codec.pack(D, I, self.id_base)
             recv, work = self._exchange_start(P, per)
             if pending is not None:
@@ -276,6 +281,7 @@ class ShardedIndexFlat(_ShardedSearch):
             from .faiss import IndexFlat
             make_index = IndexFlat
         self.local = make_index(d, metric)
+        self.seed_sample_rows = SEED_SAMPLE_ROWS
 
     # ------------------------------------------------------------------ build
     def add_global(self, x):
@@ -297,11 +303,37 @@ class ShardedIndexFlat(_ShardedSearch):
         self.ntotal = int(ntotal)
         self._set_bases_gathered()
 
-    def search_local(self, xq, k: int):
+    def _sample_bounds(self, q, k: int, per: int):
+        """Seeds for the shard searches of one chunk. A shard that starts cold spends its first tiles
+        appending nearly everything (the running top-k threshold warms up once per shard: G times
+        per query instead of once). So every rank first searches ITS rows of the chunk (the ones it
+        will merge) against the first seed_sample_rows rows of its shard -- 1/G of the queries x a
+        small sample -- and the ranks all-gather the k-th best scores (4 bytes per query). At least k
+        items of the catalog reach that score, so it is a valid lower bound of the query's global
+        k-th best, and every shard's kernel starts from it (nrb_search_flat_seeded). Returns f32[cn]
+        or None. The decision uses only rank-independent quantities (it guards a collective)."""
+        G, m = self.world, int(self.seed_sample_rows or 0)
+        from .faiss import PATH_AUTO, PATH_TC1, PATH_TC16, _round_kp
+        if G == 1 or m <= 0 or self.ntotal // G < 4 * m or k > 112 or _round_kp(self.d) > 256 or \
+                self.local.path not in (PATH_AUTO, PATH_TC1, PATH_TC16):
+            return None
+        cn, r = q.n, self.rank
+        lo, hi = min(cn, r * per), min(cn, (r + 1) * per)
+        none = 3.4028234663852886e38 if self.metric_type == 1 else -3.4028234663852886e38
+        mine = torch.full((per,), none, dtype=torch.float32, device=q.device)
+        if hi > lo:
+            Ds, _ = self.local.search_packed(q, k, 0, rows=m, qrange=(lo, hi - lo))
+            mine[: hi - lo] = Ds[:, k - 1]
+        full = torch.empty(G * per, dtype=torch.float32, device=q.device)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return full[:cn].contiguous()
+
+    def search_local(self, xq, k: int, per: int | None = None):
         if self._cuda_index:
             from .faiss import PackedMatrix
             q = PackedMatrix.from_tensor(xq, planes=self.local._query_planes(k))  # K0 on the fresh chunk
-            return self.local.search_packed(q, k, self.id_base)
+            seed = self._sample_bounds(q, k, per) if per is not None else None
+            return self.local.search_packed(q, k, self.id_base, seed=seed)
         D, I = self.local.search(np.ascontiguousarray(xq), k)
         I = torch.as_tensor(I)
         return torch.as_tensor(D), torch.where(I >= 0, I + self.id_base, I)
@@ -531,7 +563,7 @@ class ShardedIndexIVFFlat(_ShardedSearch):
         self.ntotal = int(ntotal)
         self._set_bases_gathered()
 
-    def search_local(self, xq, k: int):
+    def search_local(self, xq, k: int, per: int | None = None):
         self.local.nprobe = self.nprobe
         if self._cuda_index:
             D, I = self.local.search(xq, k)  # ids = local insertion rows
