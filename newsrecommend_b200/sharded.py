@@ -28,8 +28,12 @@ import torch
 import torch.distributed as dist
 
 CHUNK_WAVES = 7  # queries per chunk = CHUNK_WAVES full waves of the search kernel (7 x 18,944)
-# rows of the sample pass that seeds every shard's running bounds (0: off; NRB_SEED_ROWS overrides for A/B runs)
-SEED_SAMPLE_ROWS = int(os.environ.get("NRB_SEED_ROWS", "8192"))
+# Rows of the sample pass that seeds every shard's running bounds. OFF by default: measured on 2 B200
+# (profiles/r02_seed_n2_*.json) the sample pass costs what it saves -- a cold 32-tile unit is ~0.5 M
+# cycles whether it runs as the sample or as the head of the shard scan, so only the G-fold reuse
+# pays, and at G = 2 the extra launches + the all-gather make it a net loss (6.19 vs 5.74 ms / step).
+# NRB_SEED_ROWS=8192 turns it on (A/B runs, larger G).
+SEED_SAMPLE_ROWS = int(os.environ.get("NRB_SEED_ROWS", "0"))
 
 
 def shard_range(nb: int, world: int, rank: int) -> tuple[int, int]:
