@@ -8,7 +8,9 @@ per step (the search Retrieval.py:32 performs per user, in its north-star IndexF
 * our arm: one process per GPU (torchrun for N > 1). N = 1: the whole catalog on one B200.
   N > 1 ("strong" scaling: the job is fixed, value = queries of one step x steps /
   max-over-ranks device time): the N ranks form N/S replica groups of S catalog shards each
-  (--shards S, default S = N: north_star item 4). Inside a group the catalog rows are sharded,
+  (--shards S; default: shards of at least 180,000 rows and at least 2 of them, i.e. S = 2 for this
+  364,047-row catalog -- north_star item 4 with the shard size a deployment would pick; S = N and
+  S = 1 are timed beside it as `other_decompositions`). Inside a group the catalog rows are sharded,
   every rank searches the group's queries on its shard, the per-shard results travel as 8-byte
   (score, local row) words in an NCCL all-to-all BY QUERY RANGE and each rank merges its own
   query range (K4). The query batch is split over the replica groups. --shards 1 is the
@@ -38,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NB, D, NQ, K = 364_047, 250, 50_000, 50
+MIN_SHARD_ROWS = 180_000  # default layout: catalog shards are not cut smaller than this (see run_ours)
 METRIC = "queries/s, top-50 IP over 364k x 250 items (flat exact search)"
 WORKLOAD = "flat_ip_top50: 50,000 queries x 364,047 items x 250-d fp32 (BASELINE configs[0], the config the metric is quoted on)"
 ALG_FLOP = 2.0 * NQ * NB * D  # 9.101e12 per step: padding and the 3x TF32 passes not counted
@@ -406,22 +409,30 @@ def run_ours(args):
             s += f"; {run['R']} replica groups of {run['S']} shards, the query batch split over the groups"
         return s
 
-    S_main = args.shards if args.shards > 0 else world
+    # Default layout: shard the catalog only as far as a shard keeps MIN_SHARD_ROWS rows. A shard search
+    # re-discovers every query's top-k threshold from scratch, and that warm-up costs about as much
+    # as scanning 250 tiles at the steady rate: a 364k-row catalog cut 8 ways (178-tile units) never
+    # leaves it (measured: profiles/r02_bench_n8.json). Config 1 -> replica groups of 2 shards at every
+    # N > 1 (N = 2: the box is one group); a 10M-row catalog -> one group of N shards.
+    S_main = args.shards if args.shards > 0 else max(1, min(world, NB // MIN_SHARD_ROWS))
+    if world > 1 and args.shards <= 0:
+        S_main = max(2, S_main)  # the timed path of a multi-GPU run always has the exchange + K4 merge in it
     run = build(S_main)
     res = measure(run, ClockSampler(local) if rank == 0 else None)
     ms, launches, kern_ms, kern_n, clocks, e2e_s = (res[k] for k in ("ms", "launches", "kern_ms", "kern_n", "clocks", "e2e_s"))
     main_desc = describe(run)
     run = {k: v for k, v in run.items() if not callable(v)}  # drop the index (frees HBM)
-    alt = None
+    alts = []
     if world > 1 and args.alt:
-        alt_S = 1 if run["S"] > 1 else world
-        torch.cuda.empty_cache()
-        run2 = build(alt_S)
-        r2 = measure(run2)
-        alt = {"decomposition": describe(run2), "value": NQ * args.steps / (r2["ms"] / 1e3), "ms_per_step": r2["ms"] / args.steps,
-               "e2e": NQ * args.steps / r2["e2e_s"], "kernel_ms_avg": r2["kern_ms"] / max(1, r2["kern_n"]),
-               "parity_sample": r2["parity"]}
-        del run2
+        for alt_S in sorted({1, world} - {run["S"]}):
+            torch.cuda.empty_cache()
+            run2 = build(alt_S)
+            r2 = measure(run2)
+            alts.append({"decomposition": describe(run2), "shards": run2["S"], "value": NQ * args.steps / (r2["ms"] / 1e3),
+                         "ms_per_step": r2["ms"] / args.steps, "e2e": NQ * args.steps / r2["e2e_s"],
+                         "kernel_ms_avg": r2["kern_ms"] / max(1, r2["kern_n"]), "parity_sample": r2["parity"]})
+            del run2
+    alt = alts[0] if alts else None
 
     if rank == 0:
         pk = peaks()
@@ -486,12 +497,13 @@ def run_ours(args):
             "e2e": {"value": NQ * args.steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": NQ * D * 4, "d2h_bytes_per_step": NQ * K * 12},
             "gpu_launches": int(launches), "clocks": clocks, "other_decomposition": alt,
+            "other_decompositions": alts,
             "parity_sample": res["parity"],
         }
         if world == 1 and not os.environ.get("NRB_BENCH_SKIP_CPU"):  # skipped only for ncu captures
             out["cpu_baseline"] = cpu_baseline(xb, xq)
         args.out.emit(out)
-    ok = res["parity"]["ok"] and (alt is None or alt["parity_sample"]["ok"]) if rank == 0 else True
+    ok = res["parity"]["ok"] and all(a["parity_sample"]["ok"] for a in alts) if rank == 0 else True
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -520,8 +532,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shards", type=int, default=0,
-                    help="N > 1: catalog shards per replica group (default 0 = N: the whole box is one group of N "
-                         "catalog shards, north_star item 4; 1 = catalog replicated, queries split, no collective)")
+                    help="N > 1: catalog shards per replica group (default 0 = shards of >= 180,000 rows, at least 2: "
+                         "config 1 -> N/2 replica groups of 2 shards; N = the whole box is one group of N catalog "
+                         "shards; 1 = catalog replicated, queries split, no collective)")
     ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather"],
                     help="exchange step of the catalog-sharded search (all-to-all by query range, or the all-gather "
                          "north_star names literally)")
