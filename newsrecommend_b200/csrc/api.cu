@@ -89,11 +89,14 @@ struct FlatPlan {
     int S;           // source slots per query = tsplit * wgs
     int grid;
     int single;      // 1: single-CTA units (fp16 filter, one partial wave): unit c*nqt + t, no phantoms
+    int pw;          // partial row width of the filter paths: k + margin slots (wide rows for catalogs beyond a few tiles)
 };
 
 static FlatPlan plan_flat(int64_t nq, int64_t nb, int k, int path) {
-    (void)k;
     FlatPlan p;
+    // searches over a real catalog take the widest margin set the refine stage can hold (near-duplicate
+    // tolerance); the <= 4096-row searches (coarse quantizer, nearest centroid) keep the narrow rows
+    p.pw = (path == NRB_PATH_TC1 || path == NRB_PATH_TC16) ? tc1_pw(k, nb > 4096) : k;
     const bool simt = path == NRB_PATH_SIMT;
     p.wgs = simt ? 1 : 2;
     p.nqt = (int)((nq + UNIT_ROWS - 1) / UNIT_ROWS);
@@ -182,7 +185,7 @@ static FlatWs carve_flat(void* ws, const FlatPlan& p, int64_t nq, int k, int pat
     Carver c(ws);
     FlatWs w;
     const bool filt = path == NRB_PATH_TC1 || path == NRB_PATH_TC16;
-    const int pw = filt ? tc1_pw(k) : k;  // partial row width
+    const int pw = p.pw;  // partial row width
     w.units = c.take<Unit>(p.n_units);
     w.n_units = c.take<int>(1);
     w.src = c.take<int>((size_t)nq * p.S);
@@ -614,7 +617,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
         return launch_select(w.part_key, w.part_idx, w.src, p.S, q->n, k, metric, nullptr, id_base, D, I, st);
     }
     // ---- 1xTF32 / fp16 filter + exact refine, then the 3xTF32 kernel for whatever was flagged
-    const int pw = tc1_pw(k);
+    const int pw = p.pw;
     const float eps_xmax = TC1_EPS * b->max_norm;
     NRB_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, (size_t)q->n * sizeof(int), st));
     {

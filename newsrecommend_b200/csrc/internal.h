@@ -1,5 +1,6 @@
 // Internal C++ interfaces between the translation units of libnrb200.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,10 +37,18 @@ int launch_topk_tc_dev(const nrb_matrix* a, const nrb_matrix* b, const Unit* uni
 // 1xTF32 filter + exact refine (NRB_PATH_TC1): partial rows are `pw` = k + TC1_EXTRA wide and hold
 // every candidate within the error margin of the k-th; row_flags[a_row] = 1 marks rows whose
 // margin set did not fit. margin_scale = 2 * eps * max|x| (the kernel multiplies by |q|).
-constexpr int TC1_EXTRA = 32;      // margin slots per row when they fit ...
+constexpr int TC1_EXTRA = 32;      // margin slots per row when they fit (IVF scans: partial rows per (query, list)) ...
+constexpr int TC1_EXTRA_FLAT = 96; // ... flat searches: as many as the 128-entry exact stage of the refine can take
 constexpr int TC1_MIN_EXTRA = 16;  // ... never fewer than this (partial rows are at most 128 wide)
 constexpr int TC1_MAX_PW = 128;
-static inline int tc1_pw(int k) { return k + TC1_EXTRA <= TC1_MAX_PW ? k + TC1_EXTRA : TC1_MAX_PW; }
+static inline int tc1_extra() {  // NRB_TC1_EXTRA overrides the margin slots (A/B runs: scripts/bench_robustness.py)
+    static const int v = getenv("NRB_TC1_EXTRA") ? atoi(getenv("NRB_TC1_EXTRA")) : TC1_EXTRA;
+    return v < TC1_MIN_EXTRA ? TC1_MIN_EXTRA : v;
+}
+static inline int tc1_pw(int k, bool flat = false) {
+    const int extra = (flat && !getenv("NRB_TC1_EXTRA")) ? TC1_EXTRA_FLAT : tc1_extra();
+    return k + extra <= TC1_MAX_PW ? k + extra : TC1_MAX_PW;
+}
 static inline int tc1_k_ok(int k) { return k + TC1_MIN_EXTRA <= TC1_MAX_PW; }
 constexpr float TC1_EPS = 1.1f / 1024.f;  // both operands rounded to tf32 (2 * 2^-11) + accumulation slack
 int tc1_eligible(const nrb_matrix* a, const nrb_matrix* b, int k);

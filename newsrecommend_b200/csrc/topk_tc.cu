@@ -76,6 +76,7 @@ struct XchgShared {
     float margin[BM];        // in: the row's error margin (filter kernels; else 0)
     float nthr[BM];          // out: new append threshold (both warpgroups)
     uint32_t lb[BM];         // out: ordered-uint lower bound of the row's k-th key (0: none yet)
+    int ovf[BM];             // out: 1 if entries inside the row's margin had to be dropped (the query must be recomputed)
 };
 
 template <int STAGES>
@@ -207,6 +208,18 @@ __device__ __noinline__ PruneOut tighten_row_call(float* bk, int* bi, int n, int
     return o;
 }
 
+// A row whose margin set did not fit its slots is incomplete whatever happens next: its query is
+// flagged and recomputed by the exact path. Stop collecting for it -- on a near-duplicate-heavy
+// catalog such rows otherwise refill their buffers within a few tiles and run the exact-sort prune
+// over and over (measured: 13-30x slower searches at 16-64 copies per article).
+__device__ __forceinline__ void epi_abandon_row(EpiRow& st) {
+    st.flag = 1;
+    st.cnt = 0;
+    st.base = 0;
+    st.thr = __builtin_huge_valf();
+    st.cthr = st.thr;
+}
+
 // Prunes the rows of the warp named by `need` (one bit per lane = row) back to (about) their best
 // k (+ margin set), in place, and raises their thresholds.
 template <bool L2>
@@ -228,6 +241,7 @@ __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float*
             st.cthr = L2 ? o.thr : o.thr * st.sc;
             st.flag |= o.ovf;
             if (st.gslot && o.kth > NEG_INF) atomicMax(st.gslot, ordered_u32(o.kth));
+            if (o.ovf) epi_abandon_row(st);
         }
     }
 }
@@ -392,6 +406,7 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
         float *kA[NB], *kB[NB];
         int *iA[NB], *iB[NB];
         float floor_t[NB], mg[NB];
+        int ov[NB];
         if (min_new != 0) {
             const int r0 = quad * 32 + half * 16 + NB * it;
             bool quiet = true;
@@ -405,7 +420,10 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                     quiet = quiet && !(c0 > keep_max || c1 > keep_max || (c0 + c1 >= k && fr > 0));
             }
             if (quiet) {
-                if (lane < NB) xs->done[r0 + lane] = 0;
+                if (lane < NB) {
+                    xs->done[r0 + lane] = 0;
+                    xs->ovf[r0 + lane] = 0;
+                }
                 continue;  // warp-uniform
             }
         }
@@ -420,24 +438,31 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
             nB[b] = xs->cnt[1][row[b]];
             mg[b] = xs->margin[row[b]];
             floor_t[b] = fmaxf(xs->thr[0][row[b]], xs->thr[1][row[b]]);
-            // rare: a buffer beyond the 128-entry fast path is first pruned on its own
+            ov[b] = 0;
+            // rare: a buffer beyond the 128-entry fast path is first pruned on its own. If that has to
+            // drop entries INSIDE the margin (more than keep_max of them: a near-duplicate-heavy catalog),
+            // the row is reported as overflowed: its query is recomputed by the exact path.
             if (nA[b] > 128) {
                 const PruneOut o = tighten_row_call(kA[b], iA[b], nA[b], k, mg[b], keep_max, floor_t[b]);
                 nA[b] = o.kept;
+                ov[b] |= o.ovf;
                 floor_t[b] = fmaxf(floor_t[b], o.thr);
                 if (nA[b] > 128) {  // still too large (ties): exact prune to the best keep_max
                     const PruneOut e = prune_row_call(kA[b], iA[b], nA[b], k, mg[b], keep_max, keep_max, kA[b], iA[b], floor_t[b]);
                     nA[b] = e.kept;
+                    ov[b] |= e.ovf;
                     floor_t[b] = fmaxf(floor_t[b], e.thr);
                 }
             }
             if (nB[b] > 128) {
                 const PruneOut o = tighten_row_call(kB[b], iB[b], nB[b], k, mg[b], keep_max, floor_t[b]);
                 nB[b] = o.kept;
+                ov[b] |= o.ovf;
                 floor_t[b] = fmaxf(floor_t[b], o.thr);
                 if (nB[b] > 128) {
                     const PruneOut e = prune_row_call(kB[b], iB[b], nB[b], k, mg[b], keep_max, keep_max, kB[b], iB[b], floor_t[b]);
                     nB[b] = e.kept;
+                    ov[b] |= e.ovf;
                     floor_t[b] = fmaxf(floor_t[b], e.thr);
                 }
             }
@@ -546,6 +571,7 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                 xs->nthr[row[b]] = thr;
                 xs->lb[row[b]] = lo[b];
                 xs->done[row[b]] = 1;
+                xs->ovf[row[b]] = ov[b];
             }
         }
         __syncwarp();
@@ -871,6 +897,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                     st.cthr = L2 ? st.thr : st.thr * st.sc;
                     const uint32_t lbu = xs->lb[row];
                     if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
+                    if (NEED_QN && xs->ovf[row] && live) epi_abandon_row(st);
                 }
             }
         }
@@ -899,6 +926,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 st.cnt = xs->cnt[wg][row];
                 const uint32_t lbu = xs->lb[row];
                 if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
+                if (xs->ovf[row] && live) epi_abandon_row(st);
             }
             if (st.cnt > A.pw) {  // the margin set does not fit: the query is recomputed by the exact path
                 st.flag = 1;
