@@ -230,6 +230,24 @@ struct ProfScope {
 
 static int resolve_path(int path) { return path == NRB_PATH_SIMT ? NRB_PATH_SIMT : NRB_PATH_TC; }
 
+// The fallback of the filter paths (a handful of flagged queries recomputed by the 3xTF32 pipeline)
+// takes its scratch from the stream-ordered allocator. The device's default memory pool releases
+// freed memory back to the OS at the next synchronisation (release threshold 0), so every search with
+// even ONE flagged query paid ~10 ms for mapping ~100 MB again (measured: scripts/bench_robustness.py,
+// 16 copies per article: 19 ms per 50,000 queries of which 9 ms kernels). Keep the pool's memory.
+static void keep_pool_memory() {
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done[dev] = true;
+}
+
 static std::atomic<long long> g_fallback_queries{0};
 
 // ------------------------------------------------------------------------------ IVF grouping
@@ -648,6 +666,7 @@ static int search_flat_impl(const nrb_matrix* q, const nrb_matrix* b, int metric
     char* tmp = nullptr;
     const size_t tmp_bytes = 3 * align_up(plane, 256) + align_up((size_t)nflag * 4, 256) +
                              align_up((size_t)nflag * k * 4, 256) + align_up((size_t)nflag * k * 8, 256) + wsb2;
+    keep_pool_memory();
     NRB_CUDA_CHECK(cudaMallocAsync((void**)&tmp, tmp_bytes, st));
     Carver c(tmp);
     float* fhi = c.take<float>((size_t)nflag * q->kp);
@@ -866,6 +885,7 @@ static int ivf_search_impl(const nrb_matrix* q, const nrb_matrix* lists, const i
     const size_t tmp_bytes = 2 * align_up(plane, 256) + align_up((size_t)nflag * 4, 256) +
                              align_up((size_t)nflag * nprobe * 8, 256) + align_up((size_t)nflag * k * 4, 256) +
                              align_up((size_t)nflag * k * 8, 256) + wsb2;
+    keep_pool_memory();
     NRB_CUDA_CHECK(cudaMallocAsync((void**)&tmp, tmp_bytes, st));
     Carver c(tmp);
     float* fhi = c.take<float>((size_t)nflag * q->kp);

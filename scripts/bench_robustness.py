@@ -40,18 +40,23 @@ def run(name, xb, xq):
         step()
     torch.cuda.synchronize()
     f0 = int(_lib.lib.nrb_fallback_query_count())
+    _lib.profile_enable(True)
+    _lib.profile_read()
     t0 = time.perf_counter()
     reps = 5
     for _ in range(reps):
         Dd, Id = step()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
+    kms, kn = _lib.profile_read()
+    _lib.profile_enable(False)
     fb = (int(_lib.lib.nrb_fallback_query_count()) - f0) // reps
     ns = 1024
     pick = np.linspace(0, NQ - 1, ns).astype(np.int64)
     Do, Io = fo.knn_fast(xq[pick], xb, K, 0)
     rep = compare_topk(Dd[pick].cpu().numpy(), Id[pick].cpu().numpy(), Do, Io, 0)
-    return dict(case=name, qps=NQ / dt, ms=dt * 1e3, fallback_queries=fb, fallback_rate=fb / NQ,
+    return dict(case=name, qps=NQ / dt, ms=dt * 1e3, k2_kernel_ms=kms / reps, k2_launches_per_search=kn / reps,
+                fallback_queries=fb, fallback_rate=fb / NQ,
                 parity_ok=bool(rep["ok"]), recall=rep["recall"], max_rel_score_err=rep["max_rel_score_err"])
 
 
@@ -61,7 +66,7 @@ xq = synth.user_profiles(xb, topics, NQ, 43)
 out.append(run("g_skew (benchmark data)", xb, xq))
 out.append(run("g_iso (isotropic Gaussian)", synth.g_iso(NB, D, 1234), synth.g_iso(NQ, D, 1235)))
 rng = np.random.default_rng(7)
-for m in (4, 16, 64):
+for m in [int(a) for a in os.environ.get("NRB_DUPS", "4,16,64").split(",")]:
     nbase = NB // m
     base = xb[:nbase]
     rep_rows = np.tile(np.arange(nbase), m + 1)[:NB]

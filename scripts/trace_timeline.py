@@ -19,6 +19,14 @@ from newsrecommend_b200 import _lib, synth  # noqa: E402
 NB, NQ, D, K = 364047, int(os.environ.get("NQ", 50000)), 250, 50
 xb, topics = synth.g_skew(NB, D, 42, return_topics=True)
 xq = synth.user_profiles(xb, topics, NQ, 43)
+if os.environ.get("NRB_TRACE_DUP"):  # near-duplicate-heavy catalog: m copies per article (scripts/bench_robustness.py)
+    m = int(os.environ["NRB_TRACE_DUP"])
+    rng = np.random.default_rng(7)
+    base = xb[: NB // m]
+    rows = np.tile(np.arange(NB // m), m + 1)[:NB]
+    xb = np.ascontiguousarray((base[rows] * (1.0 + 1e-4 * rng.standard_normal((NB, 1), dtype=np.float32))
+                               + 1e-4 * np.linalg.norm(base[rows], axis=1, keepdims=True) / np.sqrt(D)
+                               * rng.standard_normal((NB, D), dtype=np.float32)).astype(np.float32))
 idx = nf.IndexFlatIP(D)
 idx.add(xb)
 q = nf.PackedMatrix.from_tensor(torch.from_numpy(xq).cuda(), planes=idx._query_planes(K))
