@@ -140,7 +140,7 @@ struct EpiRow {
     int cnt;
     int base;      // entries kept by the row's last prune (nothing was appended while cnt == base)
     float thr;     // append threshold: kth - margin (NEG_INF until k candidates exist)
-    float cthr;    // thr in the domain the pass mask compares in (IP: thr * sc, L2: thr)
+    float cthr;    // thr in the domain the pass mask compares in (IP: thr * sc; L2: thr + |q|^2, against 2 q.x - |x|^2)
     float sc;      // accumulator = sc * (q . x): product of the operands' power-of-two fp16 scales, else 1
     float inv;     // 1 / sc (exact)
     float qn;      // squared query norm (L2 keys, margins)
@@ -238,7 +238,7 @@ __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float*
             st.cnt = o.kept;
             st.base = o.kept;
             st.thr = o.thr;
-            st.cthr = L2 ? o.thr : o.thr * st.sc;
+            st.cthr = L2 ? o.thr + st.qn : o.thr * st.sc;
             st.flag |= o.ovf;
             if (st.gslot && o.kth > NEG_INF) atomicMax(st.gslot, ordered_u32(o.kth));
             if (o.ovf) epi_abandon_row(st);
@@ -264,7 +264,9 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
 #pragma unroll
     for (int i = 0; i < 32; i++) {
         float x = __uint_as_float(v[i]);  // IP: stays in the accumulator's (scaled) domain
-        if (L2) x = -fmaxf(fmaf(x, m2inv, st.qn + nrm[c0 + i]), 0.f);
+        // L2: ONE fma per element -- t = 2 q.x - |x|^2 (nrm holds -|x|^2); the row constant |q|^2 lives in
+        // the threshold (cthr = thr + |q|^2) and the clamp at distance 0 is applied to appended keys only
+        if (L2) x = fmaf(x, m2inv, nrm[c0 + i]);
         if (!FULL && c0 + i >= valid) x = NEG_INF;
         f[i] = x;
     }
@@ -284,7 +286,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 if (f[8 * j + i] > st.cthr) {
-                    myk[st.cnt] = f[8 * j + i] * ksc;
+                    myk[st.cnt] = L2 ? fminf(f[8 * j + i] - st.qn, 0.f) : f[8 * j + i] * ksc;
                     myi[st.cnt] = id0 + c0 + 8 * j + i;
                     st.cnt++;
                 }
@@ -307,7 +309,7 @@ template <bool L2>
 __device__ __forceinline__ void epi_tile_ragged(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
                                                 float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
                                                 int lane) {
-    const float m2inv = -2.f * st.inv;
+    const float m2inv = 2.f * st.inv;  // epi_chunk: t = acc * (2 / scale) - |x|^2
 #pragma unroll 1
     for (int c0 = 0; c0 < HALF_N; c0 += 32) {
         if (c0 >= valid) break;  // warp-uniform
@@ -628,7 +630,7 @@ __device__ __noinline__ OneShotOut single_tile_call(uint32_t taddr0, int valid, 
 #pragma unroll
     for (int i = 0; i < HALF_N; i++) {
         float x = f[i];
-        if (L2) x = -fmaxf(fmaf(x, m2inv, qn + nrm[i]), 0.f);
+        if (L2) x = -fmaxf(fmaf(x, m2inv, qn - nrm[i]), 0.f);  // nrm holds -|x|^2
         const bool ok = i < valid;
         f[i] = ok ? x : NEG_INF;
         mn = ok ? fminf(mn, x) : mn;
@@ -688,7 +690,7 @@ __device__ __forceinline__ void epi_stage_norms(float* nrm, const float* b_norms
         // stage the norms of this warpgroup's 128 columns (one per thread); the warpgroup's named
         // barrier also orders reuse of the buffer
         const int64_t br = (int64_t)un.b_row0 + col_base + etid;
-        nrm[etid] = (etid < valid && br < b_total) ? b_norms[br] : 0.f;
+        nrm[etid] = (etid < valid && br < b_total) ? -b_norms[br] : 0.f;  // NEGATED: the addend of the epilogue's fma
         if (wg == 0)
             asm volatile("bar.sync 1, 128;" ::: "memory");
         else
@@ -816,7 +818,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             NRB_TR(warp - EPI_WARP0 + 1, gt, 1);
             if (st.gslot) {
                 st.thr = fmaxf(st.thr, from_ordered_u32(g_raw) - st.margin);
-                st.cthr = L2 ? st.thr : st.thr * st.sc;
+                st.cthr = L2 ? st.thr + st.qn : st.thr * st.sc;
             }
             const uint32_t taddr0 = taddr_wg + (uint32_t)(acc * BN);
             // hands this warp's part of the accumulator back to the MMA warp
@@ -838,7 +840,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 st.base = st.cnt;
                 if (first_shot && live && o.lb > NEG_INF) {  // the unit goes on: appends continue above the bound
                     st.thr = fmaxf(st.thr, o.lb - st.margin);
-                    st.cthr = L2 ? st.thr : st.thr * st.sc;
+                    st.cthr = L2 ? st.thr + st.qn : st.thr * st.sc;
                 }
                 NRB_TR(warp - EPI_WARP0 + 1, gt, 2);
                 if (wg == 0 && st.gslot && o.lb > NEG_INF) atomicMax(st.gslot, ordered_u32(o.lb));
@@ -856,7 +858,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 ptx::tmem_ld_wait();
                 release();
                 NRB_TR(warp - EPI_WARP0 + 1, gt, 2);
-                const float m2inv = -2.f * st.inv;
+                const float m2inv = 2.f * st.inv;  // epi_chunk: t = acc * (2 / scale) - |x|^2
                 const int id0 = un.b_row0 + col_base;
                 epi_chunk<L2, true>(v0, 0, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
                 epi_chunk<L2, true>(v1, 32, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
@@ -894,7 +896,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                     st.cnt = xs->cnt[wg][row];
                     st.base = st.cnt;
                     st.thr = xs->nthr[row];
-                    st.cthr = L2 ? st.thr : st.thr * st.sc;
+                    st.cthr = L2 ? st.thr + st.qn : st.thr * st.sc;
                     const uint32_t lbu = xs->lb[row];
                     if (wg == 0 && st.gslot && lbu != 0u) atomicMax(st.gslot, lbu);
                     if (NEED_QN && xs->ovf[row] && live) epi_abandon_row(st);
