@@ -115,6 +115,51 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
     }
 }
 
+// Candidate storage views. The SIMT kernel keeps keys and ids in two arrays (SoA); the tcgen05
+// kernels keep one array of 8-byte (key, idx) entries (AoS): an append is ONE predicated 64-bit store
+// (half the store wavefronts of the first tiles of a cold unit, where 32 lanes write 32 different
+// rows, and 6 instead of 8 instructions per expanded element), a prune loads one 64-bit word per entry.
+struct SoAView {
+    float* k;
+    int* i;
+    __device__ __forceinline__ void load(int e, float& key, int& idx) const {
+        key = k[e];
+        idx = i[e];
+    }
+    __device__ __forceinline__ void store(int e, float key, int idx) const {
+        k[e] = key;
+        i[e] = idx;
+    }
+    __device__ __forceinline__ const void* base() const { return k; }
+};
+struct AoSView {
+    uint2* p;
+    __device__ __forceinline__ void load(int e, float& key, int& idx) const {
+        const uint2 v = p[e];
+        key = __uint_as_float(v.x);
+        idx = (int)v.y;
+    }
+    __device__ __forceinline__ void store(int e, float key, int idx) const {
+        p[e] = make_uint2(__float_as_uint(key), (uint32_t)idx);
+    }
+    __device__ __forceinline__ const void* base() const { return p; }
+};
+// Output of a prune: back into the AoS buffer (p != null) or into a pair of partial-row arrays.
+struct EitherView {
+    uint2* p;
+    float* k;
+    int* i;
+    __device__ __forceinline__ void store(int e, float key, int idx) const {
+        if (p) {
+            p[e] = make_uint2(__float_as_uint(key), (uint32_t)idx);
+        } else {
+            k[e] = key;
+            i[e] = idx;
+        }
+    }
+    __device__ __forceinline__ const void* base() const { return p ? (const void*)p : (const void*)k; }
+};
+
 // Warp-cooperative prune of one row's candidate buffer ((bk, bi) must have 32*R readable entries:
 // the candidate buffers always have CAND_CAP). Sorts the first `n` entries of (bk, bi)
 // best-first, finds kth = key of the k-th best (NEG_INF while fewer than k exist) and keeps the
@@ -126,20 +171,16 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t (&c)[R], int lane) {
 // top-k prune. All 32 lanes must call with identical arguments.
 // R = registers per lane: the sort covers 32*R entries, so n must be <= 32*R (width may be larger:
 // the rest of the output row is padding). When ok aliases bk, width must be <= 32*R.
-template <int R = CAND_CAP / 32>
-__device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi, int n, int k, float margin,
-                                                  int keep_max, int width, float* ok, int* oi, int lane,
-                                                  int* kept, bool* overflow, float floor_thr = NEG_INF,
-                                                  float* kth_out = nullptr) {
+template <int R, class In, class Out>
+__device__ __forceinline__ float warp_prune_row_v(const In in, int n, int k, float margin, int keep_max, int width,
+                                                  const Out out, int lane, int* kept, bool* overflow,
+                                                  float floor_thr = NEG_INF, float* kth_out = nullptr) {
     // unconditional loads (32*R <= CAND_CAP entries are always allocated; the tail is masked): the
     // compiler batches them, whereas predicated loads were issued a few at a time
     float rk[R];
     int ri[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        rk[i] = bk[i * 32 + lane];
-        ri[i] = bi[i * 32 + lane];
-    }
+    for (int i = 0; i < R; i++) in.load(i * 32 + lane, rk[i], ri[i]);
     uint64_t c[R];
 #pragma unroll
     for (int i = 0; i < R; i++) c[i] = (i * 32 + lane < n) ? pack_cand(rk[i], ri[i]) : empty_cand();
@@ -181,16 +222,22 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
         const int e = i * 32 + lane;
         if (e < width) {
             const bool keep = e < cnt;
-            ok[e] = keep ? cand_key(c[i]) : NEG_INF;
-            oi[e] = keep ? cand_idx(c[i]) : -1;
+            out.store(e, keep ? cand_key(c[i]) : NEG_INF, keep ? cand_idx(c[i]) : -1);
         }
     }
-    for (int e = 32 * R + lane; e < width; e += 32) {  // output wider than the sort: padding
-        ok[e] = NEG_INF;
-        oi[e] = -1;
-    }
+    for (int e = 32 * R + lane; e < width; e += 32) out.store(e, NEG_INF, -1);  // output wider than the sort: padding
     __syncwarp();
     return fmaxf(thr, floor_thr);  // threshold for further appends
+}
+
+// The two-array form (SIMT kernel, tests).
+template <int R = CAND_CAP / 32>
+__device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi, int n, int k, float margin,
+                                                  int keep_max, int width, float* ok, int* oi, int lane,
+                                                  int* kept, bool* overflow, float floor_thr = NEG_INF,
+                                                  float* kth_out = nullptr) {
+    return warp_prune_row_v<R>(SoAView{const_cast<float*>(bk), const_cast<int*>(bi)}, n, k, margin, keep_max, width,
+                               SoAView{ok, oi}, lane, kept, overflow, floor_thr, kth_out);
 }
 
 // Cheap mid-unit prune: instead of sorting, find a LOWER BOUND lb of the row's k-th best key by
@@ -201,17 +248,14 @@ __device__ __forceinline__ float warp_prune_row_m(const float* bk, const int* bi
 // a valid bound of the k-th minus the margin, hence outside the final top-k / margin set.
 // Returns the new append threshold; *kept = entries left in (bk, bi); *lb_u = ordered-uint lower
 // bound of the k-th (0 while fewer than k entries exist). n <= 32*R. All lanes call together.
-template <int R>
-__device__ __forceinline__ float warp_tighten_row(float* bk, int* bi, int n, int k, float margin, float floor_thr,
+template <int R, class Buf>
+__device__ __forceinline__ float warp_tighten_row(const Buf buf, int n, int k, float margin, float floor_thr,
                                                   int lane, int* kept, uint32_t* lb_u) {
     constexpr int SLACK = 3;
     float rk[R];
     int id[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) {  // unconditional, batched loads (see warp_prune_row_m)
-        rk[i] = bk[i * 32 + lane];
-        id[i] = bi[i * 32 + lane];
-    }
+    for (int i = 0; i < R; i++) buf.load(i * 32 + lane, rk[i], id[i]);  // unconditional, batched loads (see warp_prune_row_v)
     uint32_t u[R];
 #pragma unroll
     for (int i = 0; i < R; i++) u[i] = (i * 32 + lane < n) ? ordered_u32(rk[i]) : 0u;  // 0 sorts below every float
@@ -252,11 +296,7 @@ __device__ __forceinline__ float warp_tighten_row(float* bk, int* bi, int n, int
         const float key = from_ordered_u32(u[i]);
         const bool keep = (u[i] != 0u) && key >= thr;
         const uint32_t b = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int pos = base + __popc(b & lt);
-            bk[pos] = key;
-            bi[pos] = id[i];
-        }
+        if (keep) buf.store(base + __popc(b & lt), key, id[i]);
         base += __popc(b);
     }
     __syncwarp();

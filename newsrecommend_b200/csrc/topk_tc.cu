@@ -157,18 +157,19 @@ struct PruneOut {
 // One row's prune behind a real call: the kernel has three call sites (in-tile overflow guard,
 // scheduled prune, unit end) and two sort widths; inlining all of them multiplies the unrolled
 // bitonic networks and the kernel no longer fits the instruction cache.
-__device__ __noinline__ PruneOut prune_row_call(const float* bk, const int* bi, int n, int k, float margin,
-                                                int keep_max, int width, float* ok, int* oi, float floor_thr) {
+// Input: the row's AoS candidate buffer. Output: back into that buffer (ob == b: in place) or into a
+// partial row (ok, oi) when ob is null.
+__device__ __noinline__ PruneOut prune_row_call(const uint2* b, int n, int k, float margin, int keep_max, int width,
+                                                uint2* ob, float* ok, int* oi, float floor_thr) {
     const int lane = threadIdx.x & 31;
+    const AoSView in{const_cast<uint2*>(b)};
+    const EitherView out{ob, ok, oi};
     PruneOut o;
     bool ovf;
     // the sort is sized by the entries present: a row whose threshold was hot from the start (later
     // lists of an IVF query, later chunks of a split catalog) ends its unit with a handful
     if (n == 0) {  // nothing buffered (dead row, or nothing beat an already hot threshold): padding only
-        for (int e = lane; e < width; e += 32) {
-            ok[e] = NEG_INF;
-            oi[e] = -1;
-        }
+        for (int e = lane; e < width; e += 32) out.store(e, NEG_INF, -1);
         __syncwarp();
         o.thr = floor_thr;
         o.kth = NEG_INF;
@@ -176,16 +177,16 @@ __device__ __noinline__ PruneOut prune_row_call(const float* bk, const int* bi, 
         o.ovf = 0;
         return o;
     }
-    const bool inplace = (ok == bk);  // in-place prunes must also cover the whole output width
+    const bool inplace = ob != nullptr;  // in-place prunes must also cover the whole output width
     if (n <= 32 && !inplace)
-        o.thr = warp_prune_row_m<1>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
+        o.thr = warp_prune_row_v<1>(in, n, k, margin, keep_max, width, out, lane, &o.kept, &ovf, floor_thr, &o.kth);
     else if (n <= 64 && !inplace)
-        o.thr = warp_prune_row_m<2>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
+        o.thr = warp_prune_row_v<2>(in, n, k, margin, keep_max, width, out, lane, &o.kept, &ovf, floor_thr, &o.kth);
     else if (n <= 128 && width <= 128)
-        o.thr = warp_prune_row_m<4>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf, floor_thr, &o.kth);
+        o.thr = warp_prune_row_v<4>(in, n, k, margin, keep_max, width, out, lane, &o.kept, &ovf, floor_thr, &o.kth);
     else
-        o.thr = warp_prune_row_m<CAND_CAP / 32>(bk, bi, n, k, margin, keep_max, width, ok, oi, lane, &o.kept, &ovf,
-                                                floor_thr, &o.kth);
+        o.thr = warp_prune_row_v<CAND_CAP / 32>(in, n, k, margin, keep_max, width, out, lane, &o.kept, &ovf, floor_thr,
+                                                &o.kth);
     o.ovf = ovf ? 1 : 0;
     return o;
 }
@@ -193,18 +194,17 @@ __device__ __noinline__ PruneOut prune_row_call(const float* bk, const int* bi, 
 // Mid-unit prune of one row, in place: the bisection/compaction fast path, and the exact sort only
 // when that leaves too many entries (heavy ties, or a margin set that does not fit).
 constexpr int TIGHTEN_MAX_KEEP = 160;
-__device__ __noinline__ PruneOut tighten_row_call(float* bk, int* bi, int n, int k, float margin, int keep_max,
-                                                  float floor_thr) {
+__device__ __noinline__ PruneOut tighten_row_call(uint2* b, int n, int k, float margin, int keep_max, float floor_thr) {
     const int lane = threadIdx.x & 31;
     PruneOut o;
     uint32_t lb;
     if (n <= 128)
-        o.thr = warp_tighten_row<4>(bk, bi, n, k, margin, floor_thr, lane, &o.kept, &lb);
+        o.thr = warp_tighten_row<4>(AoSView{b}, n, k, margin, floor_thr, lane, &o.kept, &lb);
     else
-        o.thr = warp_tighten_row<CAND_CAP / 32>(bk, bi, n, k, margin, floor_thr, lane, &o.kept, &lb);
+        o.thr = warp_tighten_row<CAND_CAP / 32>(AoSView{b}, n, k, margin, floor_thr, lane, &o.kept, &lb);
     o.kth = from_ordered_u32(lb);
     o.ovf = 0;
-    if (o.kept > TIGHTEN_MAX_KEEP) o = prune_row_call(bk, bi, o.kept, k, margin, keep_max, keep_max, bk, bi, o.thr);
+    if (o.kept > TIGHTEN_MAX_KEEP) o = prune_row_call(b, o.kept, k, margin, keep_max, keep_max, b, nullptr, nullptr, o.thr);
     return o;
 }
 
@@ -223,17 +223,14 @@ __device__ __forceinline__ void epi_abandon_row(EpiRow& st) {
 // Prunes the rows of the warp named by `need` (one bit per lane = row) back to (about) their best
 // k (+ margin set), in place, and raises their thresholds.
 template <bool L2>
-__device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float* ck, int* ci, int k, int keep_max,
-                                               int lane) {
+__device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, uint2* cb, int k, int keep_max, int lane) {
     while (need) {
         const int src = __ffs(need) - 1;
         need &= need - 1;
         const int n = __shfl_sync(0xffffffffu, st.cnt, src);
         const float mg = __shfl_sync(0xffffffffu, st.margin, src);
         const float fl = __shfl_sync(0xffffffffu, st.thr, src);  // entries were appended above it
-        float* rk = ck + (int64_t)src * CAND_CAP;
-        int* ri = ci + (int64_t)src * CAND_CAP;
-        const PruneOut o = tighten_row_call(rk, ri, n, k, mg, keep_max, fl);
+        const PruneOut o = tighten_row_call(cb + (int64_t)src * CAND_CAP, n, k, mg, keep_max, fl);
         if (lane == src) {
             st.cnt = o.kept;
             st.base = o.kept;
@@ -258,8 +255,8 @@ __device__ __forceinline__ void epi_prune_rows(unsigned need, EpiRow& st, float*
 //     access is an L2 round trip on the epilogue's critical path.
 template <bool L2, bool FULL>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int valid, int id0, const float* nrm,
-                                          float m2inv, EpiRow& st, float* ck, int* ci, float* myk, int* myi,
-                                          int k, int keep_max, int lane) {
+                                          float m2inv, EpiRow& st, uint2* cb, uint2* myb, int k, int keep_max,
+                                          int lane) {
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) {
@@ -285,9 +282,9 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
         if (g[j] > st.cthr) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                if (f[8 * j + i] > st.cthr) {
-                    myk[st.cnt] = L2 ? fminf(f[8 * j + i] - st.qn, 0.f) : f[8 * j + i] * ksc;
-                    myi[st.cnt] = id0 + c0 + 8 * j + i;
+                if (f[8 * j + i] > st.cthr) {  // one 64-bit store per appended entry
+                    const float key = L2 ? fminf(f[8 * j + i] - st.qn, 0.f) : f[8 * j + i] * ksc;
+                    myb[st.cnt] = make_uint2(__float_as_uint(key), (uint32_t)(id0 + c0 + 8 * j + i));
                     st.cnt++;
                 }
             }
@@ -295,7 +292,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
     }
     // overflow guard (rare once the prune schedule is running): a chunk adds at most 32 entries
     const unsigned need = __ballot_sync(0xffffffffu, st.cnt > CAND_CAP - 32);
-    if (need) epi_prune_rows<L2>(need, st, ck, ci, k, keep_max, lane);
+    if (need) epi_prune_rows<L2>(need, st, cb, k, keep_max, lane);
 }
 
 // The ragged last tile of a unit (fewer than 128 valid columns in this warpgroup's half), chunk
@@ -304,11 +301,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
 //   valid   number of valid item columns in this half
 //   id0     item row index of column 0 of the half
 //   nrm     item norms of the half in shared memory (L2 only)
-//   ck/ci   candidate buffers of this warp's 32 rows; myk/myi = this lane's row
+//   cb      candidate buffers of this warp's 32 rows ((key, idx) entries); myb = this lane's row
 template <bool L2>
 __device__ __forceinline__ void epi_tile_ragged(uint32_t taddr0, int valid, int id0, const float* nrm, EpiRow& st,
-                                                float* ck, int* ci, float* myk, int* myi, int k, int keep_max,
-                                                int lane) {
+                                                uint2* cb, uint2* myb, int k, int keep_max, int lane) {
     const float m2inv = 2.f * st.inv;  // epi_chunk: t = acc * (2 / scale) - |x|^2
 #pragma unroll 1
     for (int c0 = 0; c0 < HALF_N; c0 += 32) {
@@ -316,21 +312,21 @@ __device__ __forceinline__ void epi_tile_ragged(uint32_t taddr0, int valid, int 
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr0 + c0, v);
         ptx::tmem_ld_wait();
-        epi_chunk<L2, false>(v, c0, valid, id0, nrm, m2inv, st, ck, ci, myk, myi, k, keep_max, lane);
+        epi_chunk<L2, false>(v, c0, valid, id0, nrm, m2inv, st, cb, myb, k, keep_max, lane);
     }
 }
 
 // Unit finished: the warp's 32 rows, best-first, into the unit's partial rows (`pw` entries
 // per row: the best k plus, for the margin filter, everything within the margin of the k-th).
-__device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int64_t prow0, int k, int pw,
-                                             float* part_key, int* part_idx, int lane) {
+__device__ __forceinline__ void epi_unit_end(EpiRow& st, uint2* cb, int64_t prow0, int k, int pw, float* part_key,
+                                             int* part_idx, int lane) {
     for (int src = 0; src < 32; src++) {
         const int n = __shfl_sync(0xffffffffu, st.cnt, src);
         const float mg = __shfl_sync(0xffffffffu, st.margin, src);
         const float fl = __shfl_sync(0xffffffffu, st.thr, src);
         const int64_t o = (prow0 + src) * pw;
-        const PruneOut r = prune_row_call(ck + (int64_t)src * CAND_CAP, ci + (int64_t)src * CAND_CAP, n, k, mg, pw, pw,
-                                          part_key + o, part_idx + o, fl < __builtin_huge_valf() ? fl : NEG_INF);
+        const PruneOut r = prune_row_call(cb + (int64_t)src * CAND_CAP, n, k, mg, pw, pw, nullptr, part_key + o, part_idx + o,
+                                          fl < __builtin_huge_valf() ? fl : NEG_INF);
         if (lane == src) {
             st.flag |= r.ovf;
             if (st.gslot && r.kth > NEG_INF) atomicMax(st.gslot, ordered_u32(r.kth));
@@ -344,8 +340,8 @@ __device__ __forceinline__ void epi_unit_end(EpiRow& st, float* ck, int* ci, int
 // so the per-(unit, row) sort of the plain top-k kernels would be wasted work here -- for the short
 // units of an IVF scan it cost more than the unit's MMAs. The caller has already brought every
 // row down to at most pw entries (final union prune) or flagged it.
-__device__ __forceinline__ void epi_unit_end_unsorted(int n, const float* ck, const int* ci, int64_t prow0, int pw,
-                                                      float* part_key, int* part_idx, int* part_cnt, int lane) {
+__device__ __forceinline__ void epi_unit_end_unsorted(int n, const uint2* cb, int64_t prow0, int pw, float* part_key,
+                                                      int* part_idx, int* part_cnt, int lane) {
     part_cnt[prow0 + lane] = n;
     // rows with more than a few entries: warp-cooperative, coalesced copies
     unsigned big = __ballot_sync(0xffffffffu, n > 4);
@@ -353,21 +349,21 @@ __device__ __forceinline__ void epi_unit_end_unsorted(int n, const float* ck, co
         const int src = __ffs(big) - 1;
         big &= big - 1;
         const int nn = __shfl_sync(0xffffffffu, n, src);
-        const float* rk = ck + (int64_t)src * CAND_CAP;
-        const int* ri = ci + (int64_t)src * CAND_CAP;
+        const uint2* rb = cb + (int64_t)src * CAND_CAP;
         const int64_t o = (prow0 + src) * pw;
         for (int e = lane; e < nn; e += 32) {
-            part_key[o + e] = rk[e];
-            part_idx[o + e] = ri[e];
+            const uint2 v = rb[e];
+            part_key[o + e] = __uint_as_float(v.x);
+            part_idx[o + e] = (int)v.y;
         }
     }
     if (n <= 4) {  // the common case of a hot row: a handful of entries, copied by the row's own lane
-        const float* rk = ck + (int64_t)lane * CAND_CAP;
-        const int* ri = ci + (int64_t)lane * CAND_CAP;
+        const uint2* rb = cb + (int64_t)lane * CAND_CAP;
         const int64_t o = (prow0 + lane) * pw;
         for (int e = 0; e < n; e++) {
-            part_key[o + e] = rk[e];
-            part_idx[o + e] = ri[e];
+            const uint2 v = rb[e];
+            part_key[o + e] = __uint_as_float(v.x);
+            part_idx[o + e] = (int)v.y;
         }
     }
 }
@@ -397,16 +393,15 @@ constexpr int UT_ROWS = NRB_UT_ROWS;  // rows of a scheduled prune in flight tog
 // still yield something -- a buffer that does not fit the partial row (more than keep_max entries),
 // or at least k candidates in the union with some of them new since the row's last prune (a
 // tighter bound of the k-th for the query's other units, and fewer candidates for the refine).
-__device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, int* ci_cta, int quad, int half,
-                                                int k, int keep_max, int min_new) {
+__device__ __noinline__ void union_tighten_rows(XchgShared* xs, uint2* cb_cta, int quad, int half, int k, int keep_max,
+                                                int min_new) {
     constexpr int NB = UT_ROWS;  // rows in flight: their loads and reduction chains overlap
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll 1
     for (int it = 0; it < 16 / NB; it++) {
         int row[NB], nA[NB], nB[NB];
-        float *kA[NB], *kB[NB];
-        int *iA[NB], *iB[NB];
+        uint2 *bA[NB], *bB[NB];  // the row's buffer in warpgroup 0 / warpgroup 1
         float floor_t[NB], mg[NB];
         int ov[NB];
         if (min_new != 0) {
@@ -432,10 +427,8 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             row[b] = quad * 32 + half * 16 + NB * it + b;
-            kA[b] = ck_cta + (int64_t)row[b] * CAND_CAP;
-            iA[b] = ci_cta + (int64_t)row[b] * CAND_CAP;
-            kB[b] = kA[b] + (int64_t)BM * CAND_CAP;
-            iB[b] = iA[b] + (int64_t)BM * CAND_CAP;
+            bA[b] = cb_cta + (int64_t)row[b] * CAND_CAP;
+            bB[b] = bA[b] + (int64_t)BM * CAND_CAP;
             nA[b] = xs->cnt[0][row[b]];
             nB[b] = xs->cnt[1][row[b]];
             mg[b] = xs->margin[row[b]];
@@ -445,24 +438,24 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
             // drop entries INSIDE the margin (more than keep_max of them: a near-duplicate-heavy catalog),
             // the row is reported as overflowed: its query is recomputed by the exact path.
             if (nA[b] > 128) {
-                const PruneOut o = tighten_row_call(kA[b], iA[b], nA[b], k, mg[b], keep_max, floor_t[b]);
+                const PruneOut o = tighten_row_call(bA[b], nA[b], k, mg[b], keep_max, floor_t[b]);
                 nA[b] = o.kept;
                 ov[b] |= o.ovf;
                 floor_t[b] = fmaxf(floor_t[b], o.thr);
                 if (nA[b] > 128) {  // still too large (ties): exact prune to the best keep_max
-                    const PruneOut e = prune_row_call(kA[b], iA[b], nA[b], k, mg[b], keep_max, keep_max, kA[b], iA[b], floor_t[b]);
+                    const PruneOut e = prune_row_call(bA[b], nA[b], k, mg[b], keep_max, keep_max, bA[b], nullptr, nullptr, floor_t[b]);
                     nA[b] = e.kept;
                     ov[b] |= e.ovf;
                     floor_t[b] = fmaxf(floor_t[b], e.thr);
                 }
             }
             if (nB[b] > 128) {
-                const PruneOut o = tighten_row_call(kB[b], iB[b], nB[b], k, mg[b], keep_max, floor_t[b]);
+                const PruneOut o = tighten_row_call(bB[b], nB[b], k, mg[b], keep_max, floor_t[b]);
                 nB[b] = o.kept;
                 ov[b] |= o.ovf;
                 floor_t[b] = fmaxf(floor_t[b], o.thr);
                 if (nB[b] > 128) {
-                    const PruneOut e = prune_row_call(kB[b], iB[b], nB[b], k, mg[b], keep_max, keep_max, kB[b], iB[b], floor_t[b]);
+                    const PruneOut e = prune_row_call(bB[b], nB[b], k, mg[b], keep_max, keep_max, bB[b], nullptr, nullptr, floor_t[b]);
                     nB[b] = e.kept;
                     ov[b] |= e.ovf;
                     floor_t[b] = fmaxf(floor_t[b], e.thr);
@@ -477,12 +470,13 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
 #pragma unroll
         for (int b = 0; b < NB; b++) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < 4; i++) {  // one 64-bit load per entry
                 const int e = i * 32 + lane;
-                rk[b][i] = kA[b][e];
-                id[b][i] = iA[b][e];
-                rk[b][4 + i] = kB[b][e];
-                id[b][4 + i] = iB[b][e];
+                const uint2 va = bA[b][e], vb = bB[b][e];
+                rk[b][i] = __uint_as_float(va.x);
+                id[b][i] = (int)va.y;
+                rk[b][4 + i] = __uint_as_float(vb.x);
+                id[b][4 + i] = (int)vb.y;
             }
         }
         uint32_t u[NB][8];
@@ -554,16 +548,8 @@ __device__ __noinline__ void union_tighten_rows(XchgShared* xs, float* ck_cta, i
                 const bool keepa = (u[b][i] != 0u) && ka >= thr;
                 const bool keepb = (u[b][4 + i] != 0u) && kb >= thr;
                 const uint32_t ma = __ballot_sync(0xffffffffu, keepa), mb = __ballot_sync(0xffffffffu, keepb);
-                if (keepa) {
-                    const int pos = baseA + __popc(ma & lt);
-                    kA[b][pos] = ka;
-                    iA[b][pos] = id[b][i];
-                }
-                if (keepb) {
-                    const int pos = baseB + __popc(mb & lt);
-                    kB[b][pos] = kb;
-                    iB[b][pos] = id[b][4 + i];
-                }
+                if (keepa) bA[b][baseA + __popc(ma & lt)] = make_uint2(__float_as_uint(ka), (uint32_t)id[b][i]);
+                if (keepb) bB[b][baseB + __popc(mb & lt)] = make_uint2(__float_as_uint(kb), (uint32_t)id[b][4 + i]);
                 baseA += __popc(ma);
                 baseB += __popc(mb);
             }
@@ -599,7 +585,7 @@ struct OneShotOut {
 // memory. As a call, the caller's live state is saved once around it instead.
 template <bool L2, bool PAIR>
 __device__ __noinline__ OneShotOut single_tile_call(uint32_t taddr0, int valid, int id0, const float* nrm, float sc,
-                                                    float inv, float qn, float margin, float* myk, int* myi, int k,
+                                                    float inv, float qn, float margin, uint2* myb, int k,
                                                     XchgShared* xs, int wg, int row, int quad, uint32_t tempty_remote,
                                                     uint64_t* tempty_local) {
     const int lane = threadIdx.x & 31;
@@ -672,8 +658,7 @@ __device__ __noinline__ OneShotOut single_tile_call(uint32_t taddr0, int valid, 
 #pragma unroll
     for (int i = 0; i < HALF_N; i++) {
         if (f[i] >= cut && i < valid) {
-            myk[cnt] = f[i] * ksc;
-            myi[cnt] = id0 + i;
+            myb[cnt] = make_uint2(__float_as_uint(f[i] * ksc), (uint32_t)(id0 + i));
             cnt++;
         }
     }
@@ -712,8 +697,7 @@ struct EpiArgs {
     int* part_idx;
     int* part_cnt;  // filter kernels: partial rows are UNSORTED, part_cnt[partial row] entries each (see epi_unit_end_unsorted)
     int* row_flags;
-    float* cand_key_buf;
-    int* cand_idx_buf;
+    uint2* cand_buf;  // candidate buffers: [CTA][warpgroup][row][CAND_CAP] (key, idx) entries
     // Shared running bounds: gthr[query] (zero-initialised ordered uints) is raised by every
     // unit of the query and read back at each tile, so units that start later (IVF lists, tail
     // chunks, the second warpgroup) begin with a hot threshold instead of re-discovering it.
@@ -745,10 +729,8 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
     const int row = quad * 32 + lane;  // query row inside the tile
     const int etid = ((warp - EPI_WARP0) & 3) * 32 + lane;
     const int64_t crow0 = ((int64_t)blockIdx.x * EPI_WGS + wg) * BM + quad * 32;  // this warp's 32 buffer rows
-    float* ck = A.cand_key_buf + crow0 * CAND_CAP;
-    int* ci = A.cand_idx_buf + crow0 * CAND_CAP;
-    float* myk = ck + (int64_t)lane * CAND_CAP;
-    int* myi = ci + (int64_t)lane * CAND_CAP;
+    uint2* cb = A.cand_buf + crow0 * CAND_CAP;
+    uint2* myb = cb + (int64_t)lane * CAND_CAP;
     uint32_t tempty_remote0 = 0, tempty_remote1 = 0;  // scalars: an indexed array would live in local memory
     if (PAIR) {
         tempty_remote0 = ptx::mapa_u32(&tempty[0], 0);
@@ -834,7 +816,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             };
             if ((IVFX && one_shot) || (first_shot && t == 0)) {
                 const OneShotOut o = single_tile_call<L2, PAIR>(taddr0, valid, un.b_row0 + col_base, nrm_t, st.sc, st.inv, st.qn,
-                                                              st.margin, myk, myi, A.k, xs, wg, row, quad,
+                                                              st.margin, myb, A.k, xs, wg, row, quad,
                                                               acc ? tempty_remote1 : tempty_remote0, &tempty[acc]);
                 st.cnt = live ? o.cnt : 0;
                 st.base = st.cnt;
@@ -860,13 +842,13 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 NRB_TR(warp - EPI_WARP0 + 1, gt, 2);
                 const float m2inv = 2.f * st.inv;  // epi_chunk: t = acc * (2 / scale) - |x|^2
                 const int id0 = un.b_row0 + col_base;
-                epi_chunk<L2, true>(v0, 0, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
-                epi_chunk<L2, true>(v1, 32, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
-                epi_chunk<L2, true>(v2, 64, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
-                epi_chunk<L2, true>(v3, 96, valid, id0, nrm_t, m2inv, st, ck, ci, myk, myi, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v0, 0, valid, id0, nrm_t, m2inv, st, cb, myb, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v1, 32, valid, id0, nrm_t, m2inv, st, cb, myb, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v2, 64, valid, id0, nrm_t, m2inv, st, cb, myb, A.k, A.pw, lane);
+                epi_chunk<L2, true>(v3, 96, valid, id0, nrm_t, m2inv, st, cb, myb, A.k, A.pw, lane);
             } else {
                 if (valid > 0)
-                    epi_tile_ragged<L2>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, ck, ci, myk, myi, A.k, A.pw, lane);
+                    epi_tile_ragged<L2>(taddr0, valid, un.b_row0 + col_base, nrm_t, st, cb, myb, A.k, A.pw, lane);
                 release();
             }
             // Scheduled prune: at tile counts 1, 2, 4, 8, ... every warp of the CTA pair brings its
@@ -885,8 +867,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 NRB_TRP(warp - EPI_WARP0 + 1, 0);
                 ptx::named_bar_sync(3 + quad, 64);
                 NRB_TRP(warp - EPI_WARP0 + 1, 1);
-                union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
-                                   A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw,
+                union_tighten_rows(xs, A.cand_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw,
                                    (A.row_map || A.seeded) ? max(4, A.k >> 2) : 0);
                 NRB_TRP(warp - EPI_WARP0 + 1, 2);
                 ptx::named_bar_sync(3 + quad, 64);
@@ -907,12 +888,12 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             // hot units: rows hold a handful of entries; only rows over pw are tightened, each on its own
             // (no exchange with the partner warp, no barriers), then the rows leave unsorted
             const unsigned need = __ballot_sync(0xffffffffu, st.cnt > A.pw);
-            if (need) epi_prune_rows<L2>(need, st, ck, ci, A.k, A.pw, lane);
+            if (need) epi_prune_rows<L2>(need, st, cb, A.k, A.pw, lane);
             if (st.cnt > A.pw) {
                 st.flag = 1;
                 st.cnt = A.pw;
             }
-            epi_unit_end_unsorted(live ? st.cnt : 0, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.pw,
+            epi_unit_end_unsorted(live ? st.cnt : 0, cb, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.pw,
                                   A.part_key, A.part_idx, A.part_cnt, lane);
         } else if (NEED_QN) {
             // final union prune (rows that need one only), then the rows leave unsorted
@@ -921,8 +902,7 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
             xs->thr[wg][row] = st.thr;
             if (wg == 0) xs->margin[row] = st.margin;
             ptx::named_bar_sync(3 + quad, 64);
-            union_tighten_rows(xs, A.cand_key_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP,
-                               A.cand_idx_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw, -1);
+            union_tighten_rows(xs, A.cand_buf + (int64_t)blockIdx.x * EPI_WGS * BM * CAND_CAP, quad, wg, A.k, A.pw, -1);
             ptx::named_bar_sync(3 + quad, 64);
             if (xs->done[row]) {
                 st.cnt = xs->cnt[wg][row];
@@ -934,11 +914,10 @@ __device__ __forceinline__ void epilogue_run(const EpiArgs& A, uint64_t* tfull, 
                 st.flag = 1;
                 st.cnt = A.pw;
             }
-            epi_unit_end_unsorted(live ? st.cnt : 0, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.pw,
+            epi_unit_end_unsorted(live ? st.cnt : 0, cb, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.pw,
                                   A.part_key, A.part_idx, A.part_cnt, lane);
         } else {
-            epi_unit_end(st, ck, ci, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key,
-                         A.part_idx, lane);
+            epi_unit_end(st, cb, ((int64_t)u * EPI_WGS + wg) * UNIT_ROWS + quad * 32, A.k, A.pw, A.part_key, A.part_idx, lane);
         }
         if (NEED_QN && st.flag && live) A.row_flags[A.row_map ? A.row_map[ar] / A.row_div : (int)ar] = 1;  // per QUERY
     }
@@ -1068,7 +1047,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         // ------------------------------------------------------------------ selection epilogue
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, n_units, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0, 0, 0};
+                   reinterpret_cast<uint2*>(cand_key_buf), gthr, row_map, row_div, nullptr, 1.f, 0, 0, 0, 0};
         epilogue_run<L2, false, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, 0);
     }
 
@@ -1208,7 +1187,7 @@ topk_tc2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         // ------------------------------------------------------------------ selection epilogue (both CTAs)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, k, 0.f, a_norms, b_norms, a_total, b_total, part_key, part_idx, nullptr, nullptr,
-                   cand_key_buf, cand_idx_buf, gthr, row_map, row_div, nullptr, 1.f, 0, 0, 0, 0};
+                   reinterpret_cast<uint2*>(cand_key_buf), gthr, row_map, row_div, nullptr, 1.f, 0, 0, 0, 0};
         epilogue_run<L2, true, false>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
@@ -1482,7 +1461,7 @@ __device__ __forceinline__ void tc3_body(const CUtensorMap& map_ah, const CUtens
         // ------------------------------------------------------------------ filter epilogue (every CTA)
         ptx::setmaxnreg_inc<232>();
         EpiArgs ea{units, *n_units_p, k, pw, margin_scale, a_norms, b_norms, a_total, b_total, part_key, part_idx,
-                   part_cnt, row_flags, cand_key_buf, cand_idx_buf, gthr, row_map, row_div, a_row_scale, b_scale, hot & 1, (hot & 2) ? 0 : 1, (hot & 4) ? 1 : 0, (hot & 8) ? 0 : 1};
+                   part_cnt, row_flags, reinterpret_cast<uint2*>(cand_key_buf), gthr, row_map, row_div, a_row_scale, b_scale, hot & 1, (hot & 2) ? 0 : 1, (hot & 4) ? 1 : 0, (hot & 8) ? 0 : 1};
         epilogue_run<L2, PAIR, true, A2>(ea, sh->tfull, sh->tempty, sh->nrm, &sh->xchg, tmem_base, warp, lane, rank);
     }
 
