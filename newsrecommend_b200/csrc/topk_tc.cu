@@ -267,24 +267,34 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int c0, int v
         if (!FULL && c0 + i >= valid) x = NEG_INF;
         f[i] = x;
     }
-    float g[4];
+#ifndef NRB_HIT_GROUP
+#define NRB_HIT_GROUP 8
+#endif
+    constexpr int GW = NRB_HIT_GROUP;  // columns per hit group (8; 4 measured: see DESIGN)
+    constexpr int NG = 32 / GW;
+    float g[NG];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float* e = f + 8 * j;
-        g[j] = fmaxf(fmaxf(fmaxf(fmaxf(e[0], e[1]), e[2]), fmaxf(fmaxf(e[3], e[4]), e[5])), fmaxf(e[6], e[7]));
+    for (int j = 0; j < NG; j++) {
+        const float* e = f + GW * j;
+        if (GW == 8)
+            g[j] = fmaxf(fmaxf(fmaxf(fmaxf(e[0], e[1]), e[2]), fmaxf(fmaxf(e[3], e[4]), e[5])), fmaxf(e[6], e[GW - 1]));
+        else
+            g[j] = fmaxf(fmaxf(fmaxf(e[0], e[1]), e[2]), e[3]);
     }
-    const float cmax = fmaxf(fmaxf(fmaxf(g[0], g[1]), g[2]), g[3]);
+    float cmax = g[0];
+#pragma unroll
+    for (int j = 1; j < NG; j++) cmax = fmaxf(cmax, g[j]);
     if (!__any_sync(0xffffffffu, cmax > st.cthr)) return;
     const float ksc = L2 ? 1.f : st.inv;  // stored keys are always unscaled
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < NG; j++) {
         if (!__any_sync(0xffffffffu, g[j] > st.cthr)) continue;  // warp-uniform
         if (g[j] > st.cthr) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (f[8 * j + i] > st.cthr) {  // one 64-bit store per appended entry
-                    const float key = L2 ? fminf(f[8 * j + i] - st.qn, 0.f) : f[8 * j + i] * ksc;
-                    myb[st.cnt] = make_uint2(__float_as_uint(key), (uint32_t)(id0 + c0 + 8 * j + i));
+            for (int i = 0; i < GW; i++) {
+                if (f[GW * j + i] > st.cthr) {  // one 64-bit store per appended entry
+                    const float key = L2 ? fminf(f[GW * j + i] - st.qn, 0.f) : f[GW * j + i] * ksc;
+                    myb[st.cnt] = make_uint2(__float_as_uint(key), (uint32_t)(id0 + c0 + GW * j + i));
                     st.cnt++;
                 }
             }
