@@ -114,7 +114,10 @@ int nrb_normalize_l2(float* x, int64_t n, int32_t d, int64_t ldx, void* stream);
  * scales on both sides, b->max_norm, kp <= 256, k <= 112), else NRB_PATH_TC1 (hi instead of h16),
  * else NRB_PATH_TC. The filter paths synchronise the stream once per call (they read back the
  * number of flagged queries); flagged queries are recomputed by NRB_PATH_TC, for which the lo
- * planes must be present or q->raw / b->hi,lo (the query rows are split on the fly). */
+ * planes must be present or q->raw / b->hi,lo (the query rows are split on the fly). That fallback
+ * takes its scratch from the stream-ordered allocator (cudaMallocAsync) and, the first time it runs
+ * on a device, raises the release threshold of the device's DEFAULT memory pool so that the pool
+ * keeps the memory between searches (a process-wide setting of that pool). */
 size_t nrb_search_flat_workspace(int64_t nq, int64_t nb, int32_t k, int32_t kp);
 int nrb_search_flat(const nrb_matrix* q, const nrb_matrix* b, int32_t metric, int32_t k,
                     int64_t id_base, float* D, int64_t* I, void* workspace,

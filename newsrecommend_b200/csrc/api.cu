@@ -1045,6 +1045,10 @@ extern "C" int nrb_kmeans_train(const nrb_matrix* x, int32_t k, int32_t niter, i
     return NRB_OK;
 }
 
+// The two host helpers below restate third-party faiss routines (facebookresearch/faiss, MIT licence:
+// utils/random.cpp rand_perm and Clustering.cpp split_clusters) because RNG-exact k-means needs their
+// exact arithmetic -- the draw order of std::mt19937, the float conversions, EPS = 1/1024. They are
+// not taken from /root/reference, which contains no native code.
 extern "C" int nrb_rand_perm_host(int32_t* perm, int64_t n, int64_t seed) {
     NRB_REQUIRE(perm && n >= 0, "rand_perm: bad arguments");
     std::mt19937 mt((unsigned)seed);
