@@ -63,6 +63,18 @@ def job_config():
                   "the 373 MB fp32 plane on the GPU, 364 MB fp32 on the CPU; B200 L2 is 126 MB)"}
 
 
+def default_shards(world: int, nb: int) -> int:
+    """Catalog shards per replica group when --shards is not given: shards keep at least MIN_SHARD_ROWS
+    rows, but a multi-GPU run always has at least 2 (its timed path contains the exchange + K4 merge);
+    the count divides the world size."""
+    if world <= 1:
+        return 1
+    s = max(2, min(world, nb // MIN_SHARD_ROWS))
+    while world % s:
+        s -= 1
+    return max(1, s)
+
+
 def make_data():
     synth = _synth()
     xb, topics = synth.g_skew(NB, D, 42, return_topics=True)
@@ -414,9 +426,7 @@ def run_ours(args):
     # as scanning 250 tiles at the steady rate: a 364k-row catalog cut 8 ways (178-tile units) never
     # leaves it (measured: profiles/r02_bench_n8.json). Config 1 -> replica groups of 2 shards at every
     # N > 1 (N = 2: the box is one group); a 10M-row catalog -> one group of N shards.
-    S_main = args.shards if args.shards > 0 else max(1, min(world, NB // MIN_SHARD_ROWS))
-    if world > 1 and args.shards <= 0:
-        S_main = max(2, S_main)  # the timed path of a multi-GPU run always has the exchange + K4 merge in it
+    S_main = args.shards if args.shards > 0 else default_shards(world, NB)
     run = build(S_main)
     res = measure(run, ClockSampler(local) if rank == 0 else None)
     ms, launches, kern_ms, kern_n, clocks, e2e_s = (res[k] for k in ("ms", "launches", "kern_ms", "kern_n", "clocks", "e2e_s"))

@@ -134,3 +134,18 @@ def test_chunk_ownership_partitions_the_batch():
                         seen[lo:hi] += 1
                 assert (seen == 1).all()
                 assert sum(c1 - c0 for c0, c1, _ in chunk_slices(nq, world, chunk)) == nq
+
+
+def test_bench_default_layout():
+    """bench.py's default multi-GPU layout: shards of >= 180,000 rows, at least 2 per replica group, a
+    divisor of the world size (config 1 -> groups of 2; a 10M-row catalog -> one group of N)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert [bench.default_shards(w, 364_047) for w in (1, 2, 4, 8)] == [1, 2, 2, 2]
+    assert [bench.default_shards(w, 10_000_000) for w in (1, 2, 4, 8)] == [1, 2, 4, 8]
+    assert bench.default_shards(3, 364_047) == 1 and bench.default_shards(6, 364_047) == 2
+    assert bench.default_shards(8, 1_000) == 2
