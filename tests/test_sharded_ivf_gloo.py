@@ -109,6 +109,16 @@ def _worker(rank, world, port, metric, mode, nb, out):
             D, I = idx.search(xq, k)
             assert np.array_equal(I.numpy(), Io), (nprobe, "merged ids differ from the single IVF index")
             assert np.allclose(D.numpy(), Do, rtol=1e-5, atol=1e-5)
+        # the same index through the *_global entry points (every rank passes the whole matrix)
+        idx3 = ShardedIndexIVFFlat(d, nlist, metric, make_index=fo.IndexFlat, make_ivf=fo.IndexIVFFlat, codec=NumpyCodec,
+                                   kmeans_ops=NumpyKMeansOps(d, nlist, metric), exchange="allgather")
+        idx3.train_global(xb, mode=mode)
+        idx3.add_global(xb)
+        assert np.array_equal(np.asarray(idx3.quantizer.xb), cent)  # deterministic: the same centroids again
+        idx3.nprobe = ref.nprobe = 2
+        D3, I3 = idx3.search(xq, k)
+        Do, Io = ref.search(xq, k)
+        assert np.array_equal(I3.numpy(), Io) and np.allclose(D3.numpy(), Do, rtol=1e-5, atol=1e-5)
         out.put((rank, True))
     except Exception as e:  # noqa: BLE001
         out.put((rank, repr(e)))
