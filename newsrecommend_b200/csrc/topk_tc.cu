@@ -726,7 +726,14 @@ struct EpiArgs {
     int seeded;       // 1: the shared bounds were seeded by the caller (nrb_search_flat_seeded)
     int first_shot_ok;  // 1: the first tile of a cold multi-tile unit takes single_tile_call (0: NRB_NO_FIRST_SHOT, A/B)
 };
-constexpr int HOT_MIN_TILES = 16;
+#ifndef NRB_HOT_MIN_TILES
+#define NRB_HOT_MIN_TILES (1 << 30)
+#endif
+// Hot units run NO scheduled prunes at all (the value was 16 tiles until the end of round 2): their rows
+// collect what beats the bound of phase A -- ~9 candidates per (query, list) pair on average, ~110 in
+// the longest lists -- and the few rows that outgrow a buffer are tightened one by one by the in-tile
+// overflow guard and at the unit's end.
+constexpr int HOT_MIN_TILES = NRB_HOT_MIN_TILES;
 
 // IVFX compiles in the short-unit machinery (hot rows, one-tile units): only the double-buffered
 // kernel (topk_tc3d_kernel) carries it, so the flat search kernels keep their exact code.
